@@ -1,0 +1,142 @@
+// kpc_abi.cpp -- extern "C" entry points of libkpopcount_gpu.so (include/kpopcount.h): argument checks and
+// exception -> error code translation around KpcEngine.  No C++ exception leaves this file.
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "kpc_engine.h"
+#include "kpc_synth.h"
+
+struct kpc_ctx {
+  KpcEngine *engine = nullptr;
+  std::string error;
+};
+
+namespace {
+thread_local std::string g_create_error;
+
+template <class F>
+int guarded(kpc_ctx *ctx, F f) {
+  if (!ctx || !ctx->engine) return KPC_E_ARG;
+  try {
+    f(*ctx->engine);
+    return KPC_OK;
+  } catch (const KpcError &e) {
+    ctx->error = e.msg;
+    return e.code;
+  } catch (const std::bad_alloc &) {
+    ctx->error = "out of host memory";
+    return KPC_E_NOMEM;
+  } catch (const std::exception &e) {
+    ctx->error = e.what();
+    return KPC_E_STATE;
+  } catch (...) {
+    ctx->error = "unknown failure";
+    return KPC_E_STATE;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int kpc_create(kpc_ctx **out, int k, int content, long long max_results_size, const char *label, int n_devices,
+               const int *device_ids) {
+  if (!out) return KPC_E_ARG;
+  *out = nullptr;
+  kpc_ctx *ctx = new (std::nothrow) kpc_ctx();
+  if (!ctx) return KPC_E_NOMEM;
+  *out = ctx;  // returned even on failure so that kpc_error() can explain; kpc_destroy() frees it
+  if (n_devices != 1) {
+    ctx->error = "this version drives one GPU per context (one context per rank for multi-GPU runs)";
+    return KPC_E_ARG;
+  }
+  try {
+    KpcEngineConfig cfg;
+    cfg.k = k;
+    cfg.content = content;
+    cfg.max_results_size = max_results_size;
+    cfg.label = label ? label : "";
+    cfg.device = device_ids ? device_ids[0] : 0;
+    ctx->engine = new KpcEngine(cfg);
+    return KPC_OK;
+  } catch (const KpcError &e) {
+    ctx->error = e.msg;
+    return e.code;
+  } catch (const std::bad_alloc &) {
+    ctx->error = "out of host memory";
+    return KPC_E_NOMEM;
+  } catch (const std::exception &e) {
+    ctx->error = e.what();
+    return KPC_E_STATE;
+  }
+}
+
+void kpc_destroy(kpc_ctx *ctx) {
+  if (!ctx) return;
+  try {
+    delete ctx->engine;
+  } catch (...) {
+  }
+  delete ctx;
+}
+
+const char *kpc_error(const kpc_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int kpc_set_sink(kpc_ctx *ctx, kpc_sink_fn sink, void *user) {
+  return guarded(ctx, [&](KpcEngine &e) { e.set_sink(sink, user); });
+}
+int kpc_staging_slots(const kpc_ctx *ctx) { return (ctx && ctx->engine) ? ctx->engine->staging_slots() : 0; }
+void *kpc_staging(kpc_ctx *ctx, int slot, size_t *capacity) {
+  void *p = nullptr;
+  guarded(ctx, [&](KpcEngine &e) { p = e.staging(slot, capacity); });
+  return p;
+}
+int kpc_begin(kpc_ctx *ctx, int format) {
+  return guarded(ctx, [&](KpcEngine &e) { e.begin(format); });
+}
+int kpc_feed(kpc_ctx *ctx, int mate, const void *bytes, size_t n, int eof) {
+  if (n && !bytes) return KPC_E_ARG;
+  return guarded(ctx, [&](KpcEngine &e) { e.feed(mate, (const uint8_t *)bytes, n, eof != 0); });
+}
+int kpc_feed_device(kpc_ctx *ctx, int mate, const void *device_bytes, size_t n, int eof) {
+  if (n && !device_bytes) return KPC_E_ARG;
+  return guarded(ctx, [&](KpcEngine &e) { e.feed_device(mate, (const uint8_t *)device_bytes, n, eof != 0); });
+}
+int kpc_set_pair_limit(kpc_ctx *ctx, long long n_pairs) {
+  return guarded(ctx, [&](KpcEngine &e) { e.set_pair_limit(n_pairs); });
+}
+long long kpc_complete_pairs(const kpc_ctx *ctx) { return (ctx && ctx->engine) ? ctx->engine->complete_pairs() : -1; }
+int kpc_end(kpc_ctx *ctx) {
+  return guarded(ctx, [&](KpcEngine &e) { e.end(); });
+}
+int kpc_finish(kpc_ctx *ctx) {
+  return guarded(ctx, [&](KpcEngine &e) { e.finish(); });
+}
+int kpc_kmers_counted(kpc_ctx *ctx, unsigned long long *out) {
+  if (!out) return KPC_E_ARG;
+  return guarded(ctx, [&](KpcEngine &e) { *out = e.kmers_counted(); });
+}
+int kpc_dense_table(kpc_ctx *ctx, void **lo_u32, void **hi_u64, unsigned long long *n_bins) {
+  if (!lo_u32 || !hi_u64 || !n_bins) return KPC_E_ARG;
+  return guarded(ctx, [&](KpcEngine &e) { e.dense_table(lo_u32, hi_u64, n_bins); });
+}
+int kpc_dense_max(kpc_ctx *ctx, unsigned long long *max_count) {
+  if (!max_count) return KPC_E_ARG;
+  return guarded(ctx, [&](KpcEngine &e) { *max_count = e.dense_max(); });
+}
+int kpc_dense_promote(kpc_ctx *ctx) {
+  return guarded(ctx, [&](KpcEngine &e) { e.dense_promote(); });
+}
+void *kpc_stream(kpc_ctx *ctx) { return (ctx && ctx->engine) ? ctx->engine->native_stream() : nullptr; }
+int kpc_sync(kpc_ctx *ctx) {
+  return guarded(ctx, [&](KpcEngine &e) { e.sync(); });
+}
+unsigned long long kpc_kernel_launches(const kpc_ctx *ctx) { return (ctx && ctx->engine) ? ctx->engine->launches() : 0; }
+const char *kpc_backend(void) { return rt_backend_name(); }
+int kpc_synth_fastq(kpc_ctx *ctx, void *device_out, unsigned long long first_record, unsigned long long n_records,
+                    unsigned long long seed) {
+  return guarded(ctx, [&](KpcEngine &e) { e.synth_fastq(device_out, first_record, n_records, seed); });
+}
+unsigned long long kpc_synth_offset(unsigned long long record) { return kpc_synth_record_offset(record); }
+
+}  // extern "C"

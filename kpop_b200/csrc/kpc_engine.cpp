@@ -1,0 +1,1101 @@
+// kpc_engine.cpp -- see kpc_engine.h.  Reference semantics cited inline (paths relative to the KPop tree).
+#include "kpc_engine.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+uint64_t pow2_at_least(uint64_t lo, uint64_t n) {  // Hashtbl.create: power_2_above 16 n
+  uint64_t s = lo;
+  while (s < n) s <<= 1;
+  return s;
+}
+size_t env_size(const char *name, size_t dflt) {
+  const char *e = getenv(name);
+  if (!e || !*e) return dflt;
+  return (size_t)strtoull(e, nullptr, 10);
+}
+// positions (offsets in the rope, ascending piece order) of the last `want` '\n' inside the first `limit` bytes
+int last_newlines(const uint8_t *const *ptr, const size_t *len, int npc, size_t limit, int want, size_t *pos) {
+  int found = 0;
+  size_t starts[4];
+  size_t off = 0;
+  for (int i = 0; i < npc; ++i) { starts[i] = off; off += len[i]; }
+  for (int i = npc - 1; i >= 0 && found < want; --i) {
+    if (starts[i] >= limit) continue;
+    size_t n = std::min(len[i], limit - starts[i]);
+    while (n > 0 && found < want) {
+      const void *q = memrchr(ptr[i], '\n', n);
+      if (!q) break;
+      size_t at = (size_t)((const uint8_t *)q - ptr[i]);
+      pos[found++] = starts[i] + at;
+      n = at;
+    }
+  }
+  return found;
+}
+// Matrix.Base.strip_external_quotes_and_check (BiOCamLib/lib/Matrix.ml:83-99); false = Quotes_in_name
+bool strip_quotes(const std::string &s0, std::string &out) {
+  size_t l = s0.size();
+  if (l == 0) { out.clear(); return true; }
+  if (l == 1 && s0[0] == '"') return false;
+  out = s0;
+  if (out[0] == '"' && out[l - 1] == '"') out = out.substr(1, l - 2);
+  return out.find('"') == std::string::npos;
+}
+
+}  // namespace
+
+// =================================================================================================
+// construction
+// =================================================================================================
+KpcEngine::KpcEngine(const KpcEngineConfig &cfg) : cfg_(cfg) {
+  if (cfg.k < 1 || cfg.max_results_size < 1) throw KpcError(KPC_E_ARG, "k and max_results_size must be positive");
+  if (cfg.content < KPC_DNA_SS || cfg.content > KPC_PROTEIN) throw KpcError(KPC_E_ARG, "unknown content");
+  if (cfg.k > kpc_max_k(cfg.content))  // KMers.ml:264-267 / 145-148
+    throw KpcError(KPC_E_K_RANGE, std::string("Invalid argument (k must be <= ") +
+                                      std::to_string(kpc_max_k(cfg.content)) + ", found " + std::to_string(cfg.k) + ")");
+  sbits_ = kpc_symbol_bits(cfg.content);
+  hex_width_ = kpc_hex_width(cfg.content, cfg.k);
+  buckets_ = pow2_at_least(16, (uint64_t)cfg.max_results_size);
+
+  // table choice
+  const int bits = sbits_ * cfg.k;
+  if (cfg.label.empty()) {
+    mode_ = TUPLE;  // -L, or -l "" (bin/KPopCount.ml:39,44)
+  } else {
+    bool dense = false;
+    if (bits <= 24 && (1ull << bits) <= buckets_) {
+      // largest number of distinct keys that can ever be in the table; the spill rule (size >= M) must be unreachable
+      unsigned __int128 distinct;
+      if (cfg.content == KPC_DNA_DS) {
+        distinct = ((unsigned __int128)1 << (2 * cfg.k)) / 2;
+        if (cfg.k % 2 == 0) distinct += ((unsigned __int128)1 << cfg.k) / 2;  // palindromes are their own reverse complement
+      } else if (cfg.content == KPC_DNA_SS) {
+        distinct = (unsigned __int128)1 << (2 * cfg.k);
+      } else {
+        distinct = 1;
+        for (int i = 0; i < cfg.k; ++i) distinct *= 22;
+      }
+      dense = distinct < (unsigned __int128)cfg.max_results_size;
+    }
+    mode_ = dense ? DENSE : HASH;
+  }
+
+  rt_init(cfg.device);
+  compute_ = rt_stream_create();
+  copy_ = rt_stream_create();
+  chunk_cap_ = env_size("KPC_CHUNK_BYTES", (size_t)64 << 20);
+  if (chunk_cap_ < 64) chunk_cap_ = 64;
+  tile_bytes_ = kpc_k_tile_bytes();
+  tile_counter_ = (uint32_t *)rt_dmalloc(64);
+  d_tmp_ = (unsigned long long *)rt_dmalloc(64 * sizeof(unsigned long long));
+  h_tmp_ = (unsigned long long *)rt_hmalloc(64 * sizeof(unsigned long long));
+  for (int m = 0; m < 2; ++m) {
+    StreamState &st = streams_[m];
+    for (int j = 0; j < 2; ++j) {
+      st.carry[j] = (KpcStreamCarry *)rt_dmalloc(sizeof(KpcStreamCarry));
+      st.hold_ev[j] = rt_event_create();
+    }
+    st.err_line = (unsigned long long *)rt_dmalloc(sizeof(unsigned long long));
+  }
+  for (int i = 0; i < kRing; ++i) ring_[i].computed = rt_event_create();
+  for (int i = 0; i < kStagingSlots; ++i) staging_ev_[i] = rt_event_create();
+
+  if (mode_ == DENSE) {
+    nbins_ = 1ull << bits;
+    dense_lo_ = (uint32_t *)rt_dmalloc(nbins_ * sizeof(uint32_t));
+    rt_memset(dense_lo_, 0, nbins_ * sizeof(uint32_t), compute_);
+  } else if (mode_ == HASH) {
+    hash_init();
+  } else {
+    d_tn_ = (unsigned long long *)rt_dmalloc(sizeof(unsigned long long));
+    rt_memset(d_tn_, 0, sizeof(unsigned long long), compute_);
+  }
+}
+
+KpcEngine::~KpcEngine() {
+  try {
+    rt_stream_sync(compute_);
+    rt_stream_sync(copy_);
+  } catch (...) {
+  }
+  for (int m = 0; m < 2; ++m) {
+    StreamState &st = streams_[m];
+    for (int j = 0; j < 2; ++j) {
+      rt_dfree(st.carry[j]);
+      if (st.hold[j]) rt_hfree(st.hold[j]);
+      rt_event_destroy(st.hold_ev[j]);
+    }
+    rt_dfree(st.err_line);
+  }
+  for (int i = 0; i < kRing; ++i) {
+    if (ring_[i].buf) rt_dfree(ring_[i].buf);
+    rt_event_destroy(ring_[i].computed);
+  }
+  for (int i = 0; i < kStagingSlots; ++i) {
+    if (staging_[i]) rt_hfree(staging_[i]);
+    rt_event_destroy(staging_ev_[i]);
+  }
+  rt_dfree(desc_); rt_dfree(tile_counter_); rt_dfree(d_tmp_); rt_hfree(h_tmp_);
+  rt_dfree(scratch_); rt_dfree(scratch2_);
+  if (h_out_) rt_hfree(h_out_);
+  rt_dfree(dense_lo_); rt_dfree(dense_hi_);
+  rt_dfree(hkeys_); rt_dfree(hcounts_); rt_dfree(hranks_); rt_dfree(d_hstat_);
+  rt_dfree(tkeys_); rt_dfree(tranks_); rt_dfree(trecs_); rt_dfree(d_tn_); rt_dfree(d_recs_);
+  rt_stream_destroy(compute_);
+  rt_stream_destroy(copy_);
+}
+
+void *KpcEngine::scratch(size_t bytes) {
+  if (bytes > scratch_cap_) {
+    rt_stream_sync(compute_);
+    rt_dfree(scratch_);
+    scratch_cap_ = bytes + bytes / 4 + 4096;
+    scratch_ = rt_dmalloc(scratch_cap_);
+  }
+  return scratch_;
+}
+void *KpcEngine::scratch2(size_t bytes) {
+  if (bytes > scratch2_cap_) {
+    rt_stream_sync(compute_);
+    rt_dfree(scratch2_);
+    scratch2_cap_ = bytes + bytes / 4 + 4096;
+    scratch2_ = rt_dmalloc(scratch2_cap_);
+  }
+  return scratch2_;
+}
+
+void KpcEngine::sync() {
+  rt_stream_sync(copy_);
+  rt_stream_sync(compute_);
+}
+
+void *KpcEngine::staging(int slot, size_t *capacity) {
+  if (slot < 0 || slot >= kStagingSlots) throw KpcError(KPC_E_ARG, "staging slot out of range");
+  if (!staging_[slot]) staging_[slot] = (uint8_t *)rt_hmalloc(chunk_cap_);
+  if (staging_busy_[slot]) {
+    rt_event_sync(staging_ev_[slot]);
+    staging_busy_[slot] = false;
+  }
+  if (capacity) *capacity = chunk_cap_;
+  return staging_[slot];
+}
+
+// =================================================================================================
+// output
+// =================================================================================================
+void KpcEngine::emit(const char *p, size_t n) {
+  if (!n) return;
+  if (!sink_) throw KpcError(KPC_E_STATE, "no sink set (kpc_set_sink)");
+  if (sink_(sink_user_, p, n) != 0) throw KpcError(KPC_E_IO, "the output sink reported a failure");
+}
+
+// device arrays (keys, counts) in final order -> text -> sink
+void KpcEngine::emit_entries(unsigned long long *keys, unsigned long long *counts, uint64_t n) {
+  if (!n) return;
+  const size_t per = (size_t)hex_width_ + 22;
+  const size_t batch = std::max<size_t>(1, ((size_t)256 << 20) / per);  // bound the device text buffer
+  if (!h_out_) {
+    h_out_cap_ = (size_t)16 << 20;
+    h_out_ = (char *)rt_hmalloc(h_out_cap_);
+  }
+  for (uint64_t i0 = 0; i0 < n; i0 += batch) {
+    const uint64_t m = std::min<uint64_t>(batch, n - i0);
+    char *d_text = (char *)scratch2(m * per + kpc_k_scan_scratch_bytes(m) + 256);
+    void *scan = d_text + ((m * per + 255) & ~(size_t)255);
+    kpc_k_format(keys + i0, counts + i0, m, hex_width_, d_text, d_tmp_ + 8, scan, compute_);
+    launches_ += 3;
+    rt_d2h(h_tmp_ + 8, d_tmp_ + 8, sizeof(unsigned long long), compute_);
+    rt_stream_sync(compute_);
+    const size_t total = (size_t)h_tmp_[8];
+    for (size_t o = 0; o < total; o += h_out_cap_) {
+      const size_t c = std::min(h_out_cap_, total - o);
+      rt_d2h(h_out_, d_text + o, c, compute_);
+      rt_stream_sync(compute_);
+      emit(h_out_, c);
+    }
+  }
+}
+
+// Hashtbl.add doubles the bucket array whenever size > 2 * buckets; the array never shrinks (clear keeps it)
+uint64_t KpcEngine::grow_buckets(uint64_t size_reached) {
+  while (size_reached > 2 * buckets_) buckets_ <<= 1;
+  return buckets_;
+}
+
+// =================================================================================================
+// input: begin / feed / end
+// =================================================================================================
+void KpcEngine::reset_stream(StreamState &st) {
+  st.fed = 0; st.hold_len = 0; st.cur = 0; st.eof = false; st.any = false; st.last_byte = '\n';
+  st.tail_unsafe = false; st.total_lines = 0; st.records = 0; st.final_recs = 0;
+  KpcStreamCarry c;
+  memset(&c, 0, sizeof c);
+  c.s1 = kpc_s1_identity();
+  c.kc = kpc_kc_identity();
+  c.kc.closed = 1;
+  c.last_byte = '\n';  // a virtual line feed before the stream makes its first byte a line start
+  memcpy(h_tmp_ + 16, &c, sizeof c);
+  rt_h2d(st.carry[0], h_tmp_ + 16, sizeof c, compute_);
+  rt_h2d(st.carry[1], h_tmp_ + 16, sizeof c, compute_);
+  rt_memset(st.err_line, 0xff, sizeof(unsigned long long), compute_);
+  rt_stream_sync(compute_);
+}
+
+void KpcEngine::begin(int format) {
+  if (failed_) throw KpcError(KPC_E_STATE, "context is in a failed state");
+  if (in_input_) throw KpcError(KPC_E_STATE, "kpc_begin while another input is open");
+  if (format != KPC_FASTA && format != KPC_FASTQ_SE && format != KPC_FASTQ_PE) throw KpcError(KPC_E_ARG, "unknown format");
+  if (!header_done_) {  // bin/KPopCount.ml:33-34: the label goes out before any input is opened
+    header_done_ = true;
+    if (!cfg_.label.empty()) {
+      std::string h = "\t" + cfg_.label + "\n";
+      emit(h.data(), h.size());
+    }
+  }
+  format_ = format;
+  in_input_ = true;
+  reset_stream(streams_[0]);
+  if (format == KPC_FASTQ_PE) reset_stream(streams_[1]);
+  for (int m = 0; m < 2; ++m) { open_recs_[m].clear(); rec_done_[m] = 0; }
+  if (mode_ == TUPLE) {  // tuples of records the previous input never completed (dropped pairs) must not leak
+    tn_ = 0;
+    rt_memset(d_tn_, 0, sizeof(unsigned long long), compute_);
+    rt_stream_sync(compute_);
+  }
+}
+
+void KpcEngine::hold_append(StreamState &st, const uint8_t *p, size_t n) {
+  const int c = st.hold_cur;
+  if (st.hold_len + n > st.hold_cap[c]) {
+    size_t ncap = std::max<size_t>(st.hold_len + n, st.hold_cap[c] * 2);
+    ncap = std::max<size_t>(ncap, std::min<size_t>(chunk_cap_ + 64, (size_t)1 << 20));
+    uint8_t *nb = (uint8_t *)rt_hmalloc(ncap);
+    if (st.hold_len) memcpy(nb, st.hold[c], st.hold_len);
+    if (st.hold[c]) rt_hfree(st.hold[c]);
+    st.hold[c] = nb;
+    st.hold_cap[c] = ncap;
+  }
+  if (n) memcpy(st.hold[c] + st.hold_len, p, n);
+  st.hold_len += n;
+}
+
+// Where to end a non-final launch inside the first `limit` bytes of the pending data.
+//  FASTA: after the last line feed (a launch never ends on a '>' that opens a line, so the one-byte look-ahead
+//         of the framing kernel stays inside the launch); no line feed at all: anywhere.
+//  FASTQ: after the 5th line feed from the end, so that every line handed over is followed by at least four
+//         more lines of the stream: its record is complete whatever comes next (Files.ml:204-217).
+size_t KpcEngine::choose_cut(StreamState &st, const Piece *pc, int npc, size_t limit) {
+  const uint8_t *ptr[4];
+  size_t len[4];
+  for (int i = 0; i < npc; ++i) { ptr[i] = pc[i].p; len[i] = pc[i].n; }
+  size_t pos[5];
+  if (format_ == KPC_FASTA) {
+    int f = last_newlines(ptr, len, npc, limit, 1, pos);
+    return f ? pos[0] + 1 : limit;
+  }
+  int f = last_newlines(ptr, len, npc, limit, 5, pos);
+  if (f == 5) return pos[4] + 1;
+  st.tail_unsafe = true;  // lines longer than a fifth of the staging size
+  return f ? pos[0] + 1 : limit;
+}
+
+KpcEngine::RingSlot &KpcEngine::next_slot() {
+  RingSlot &r = ring_[ring_next_];
+  ring_next_ = (ring_next_ + 1) % kRing;
+  if (!r.buf) r.buf = (uint8_t *)rt_dmalloc(chunk_cap_ + 256);
+  return r;
+}
+
+void KpcEngine::feed(int mate, const uint8_t *bytes, size_t n, bool eof) {
+  if (failed_) throw KpcError(KPC_E_STATE, "context is in a failed state");
+  if (!in_input_) throw KpcError(KPC_E_STATE, "kpc_feed outside kpc_begin / kpc_end");
+  if (mate < 0 || mate > 1 || (mate == 1 && format_ != KPC_FASTQ_PE)) throw KpcError(KPC_E_ARG, "bad mate index");
+  StreamState &st = streams_[mate];
+  if (st.eof) throw KpcError(KPC_E_STATE, "kpc_feed after eof");
+  if (n) { st.any = true; st.last_byte = bytes[n - 1]; }
+
+  int staging_slot = -1;
+  for (int i = 0; i < kStagingSlots; ++i)
+    if (staging_[i] && bytes >= staging_[i] && bytes < staging_[i] + chunk_cap_) staging_slot = i;
+  bool issued_from_caller = false;
+
+  const uint8_t *src = bytes;
+  size_t rem = n;
+  for (;;) {
+    const size_t pending = st.hold_len + rem;
+    if (pending < chunk_cap_ || (pending == chunk_cap_ && eof)) break;
+    // carve one non-final launch out of the first chunk_cap_ bytes of [hold | src]
+    Piece pc[2];
+    int npc = 0;
+    if (st.hold_len) pc[npc++] = Piece{st.hold[st.hold_cur], st.hold_len};
+    if (rem) pc[npc++] = Piece{src, rem};
+    size_t cut = choose_cut(st, pc, npc, chunk_cap_);
+    if (cut <= st.hold_len) {
+      // the whole launch comes out of the hold buffer (only with tiny staging sizes)
+      Piece one{st.hold[st.hold_cur], cut};
+      submit_host(st, mate, &one, 1, cut, false, false);
+      rt_stream_sync(copy_);
+      memmove(st.hold[st.hold_cur], st.hold[st.hold_cur] + cut, st.hold_len - cut);
+      st.hold_len -= cut;
+      st.hold_busy[st.hold_cur] = false;
+      continue;
+    }
+    const size_t from_src = cut - st.hold_len;
+    Piece two[2];
+    int n2 = 0;
+    if (st.hold_len) two[n2++] = Piece{st.hold[st.hold_cur], st.hold_len};
+    two[n2++] = Piece{src, from_src};
+    submit_host(st, mate, two, n2, cut, false, true);
+    issued_from_caller = true;
+    if (st.hold_len) {  // that hold buffer is in flight now: continue in the other one
+      st.hold_cur ^= 1;
+      st.hold_len = 0;
+      if (st.hold_busy[st.hold_cur]) { rt_event_sync(st.hold_ev[st.hold_cur]); st.hold_busy[st.hold_cur] = false; }
+    }
+    src += from_src;
+    rem -= from_src;
+  }
+  if (!eof) {
+    if (rem) hold_append(st, src, rem);
+  } else {
+    st.eof = true;
+    // End of file: everything that is left, plus a virtual line feed when the last line is unterminated
+    // (input_line returns such a line like any other one).
+    Piece pc[3];
+    int npc = 0;
+    size_t len = 0;
+    if (st.hold_len) { pc[npc++] = Piece{st.hold[st.hold_cur], st.hold_len}; len += st.hold_len; }
+    if (rem) { pc[npc++] = Piece{src, rem}; len += rem; issued_from_caller = true; }
+    static const uint8_t nl = '\n';
+    if (st.any && st.last_byte != '\n') { pc[npc++] = Piece{&nl, 1}; len += 1; }
+    submit_host(st, mate, pc, npc, len, true, rem != 0);
+    st.hold_len = 0;
+  }
+  if (issued_from_caller) {
+    if (staging_slot >= 0) {
+      rt_event_record(staging_ev_[staging_slot], copy_);
+      staging_busy_[staging_slot] = true;
+    } else {
+      rt_stream_sync(copy_);  // the caller may reuse its buffer as soon as we return
+    }
+  }
+}
+
+// copy the pieces into the next ring buffer and run the launch
+void KpcEngine::submit_host(StreamState &st, int mate, const Piece *pc, int npc, size_t len, bool final_launch,
+                            bool /*foreign*/) {
+  if (len > chunk_cap_ + 1) throw KpcError(KPC_E_STATE, "internal: launch larger than the staging size");
+  RingSlot &slot = next_slot();
+  if (slot.used) rt_stream_wait(copy_, slot.computed);  // the kernels that read this buffer must be done
+  size_t off = 0;
+  for (int i = 0; i < npc; ++i) {
+    if (!pc[i].n) continue;
+    rt_h2d(slot.buf + off, pc[i].p, pc[i].n, copy_);
+    off += pc[i].n;
+    for (int j = 0; j < 2; ++j)
+      if (pc[i].p == st.hold[j]) { rt_event_record(st.hold_ev[j], copy_); st.hold_busy[j] = true; }
+  }
+  rt_event ev = rt_event_create();
+  rt_event_record(ev, copy_);
+  rt_stream_wait(compute_, ev);
+  rt_event_destroy(ev);
+  // -L needs the record names: they are cut out of the host copy of the launch after the kernel has run
+  if (mode_ == TUPLE) {
+    tag_bytes_.resize(len);
+    size_t o = 0;
+    for (int i = 0; i < npc; ++i) { if (pc[i].n) memcpy(tag_bytes_.data() + o, pc[i].p, pc[i].n); o += pc[i].n; }
+  }
+  run_launch(st, mate, slot.buf, len, final_launch);
+  rt_event_record(slot.computed, compute_);
+  slot.used = true;
+}
+
+void KpcEngine::feed_device(int mate, const uint8_t *dev, size_t n, bool eof) {
+  if (failed_) throw KpcError(KPC_E_STATE, "context is in a failed state");
+  if (!in_input_) throw KpcError(KPC_E_STATE, "kpc_feed_device outside kpc_begin / kpc_end");
+  if (mode_ != DENSE) throw KpcError(KPC_E_UNSUPPORTED, "kpc_feed_device is only available on the dense-table path");
+  if (!eof) throw KpcError(KPC_E_UNSUPPORTED, "kpc_feed_device takes a whole input in one call (eof must be set)");
+  if (mate < 0 || mate > 1 || (mate == 1 && format_ != KPC_FASTQ_PE)) throw KpcError(KPC_E_ARG, "bad mate index");
+  if (((uintptr_t)dev & 15) != 0) throw KpcError(KPC_E_ARG, "device input must be 16-byte aligned");
+  StreamState &st = streams_[mate];
+  if (st.eof || st.fed || st.hold_len) throw KpcError(KPC_E_UNSUPPORTED, "kpc_feed_device cannot be mixed with kpc_feed");
+  st.eof = true;
+  if (!n) { run_launch(st, mate, dev, 0, true); return; }
+  st.any = true;
+  // find the cut between the in-place body and the tail (last lines) on a host copy of the end of the input
+  size_t win = std::min<size_t>(n, std::min<size_t>(chunk_cap_, (size_t)1 << 20));
+  std::vector<uint8_t> tail(win);
+  rt_d2h(tail.data(), dev + (n - win), win, compute_);
+  rt_stream_sync(compute_);
+  st.last_byte = tail[win - 1];
+  Piece pc{tail.data(), win};
+  size_t cut_in_win = (win == n && n <= chunk_cap_) ? 0 : choose_cut(st, &pc, 1, win);
+  size_t cut = (n - win) + cut_in_win;
+  cut &= ~(size_t)15;  // the tail launch starts at a fresh aligned buffer; the body must end on a 16-byte boundary
+  if (n - cut > chunk_cap_) throw KpcError(KPC_E_UNSUPPORTED, "lines longer than the staging size in a device input");
+  if (cut) {
+    // the body may now end in the middle of a line: legal for FASTQ (line-exact hold-back is what matters and the
+    // tail still holds the last five line feeds); for FASTA make sure it does not end on a line-opening '>'
+    if (format_ == KPC_FASTA && cut >= (n - win) + 1 && tail[cut - (n - win) - 1] == '>') {
+      if (cut >= 16) cut -= 16; else cut = 0;
+    }
+  }
+  if (cut) run_launch(st, mate, dev, cut, false);
+  RingSlot &slot = next_slot();
+  if (slot.used) rt_stream_wait(compute_, slot.computed);
+  size_t tl = n - cut;
+  rt_d2d(slot.buf, dev + cut, tl, compute_);
+  if (st.last_byte != '\n') {
+    h_tmp_[24] = '\n';
+    rt_h2d(slot.buf + tl, h_tmp_ + 24, 1, compute_);
+    tl += 1;
+  }
+  run_launch(st, mate, slot.buf, tl, true);
+  rt_event_record(slot.computed, compute_);
+  slot.used = true;
+}
+
+void KpcEngine::ensure_desc(uint64_t n_tiles) {
+  if (n_tiles <= desc_cap_) return;
+  rt_stream_sync(compute_);
+  rt_dfree(desc_);
+  desc_cap_ = n_tiles + n_tiles / 8 + 64;
+  desc_ = (KpcTileDesc *)rt_dmalloc(desc_cap_ * sizeof(KpcTileDesc));
+  rt_memset(desc_, 0, desc_cap_ * sizeof(KpcTileDesc), compute_);
+  // flags carry the launch epoch: restart it so that stale values of a previous array cannot match
+  epoch_ = 0;
+}
+
+// number of lines the final launch may use: complete records only (FASTQ.iter_se drops a record cut by EOF)
+uint64_t KpcEngine::final_line_cap(StreamState &st, const uint8_t *dev, size_t len) {
+  rt_memset(d_tmp_, 0, sizeof(unsigned long long), compute_);
+  kpc_k_count_newlines(dev, len, d_tmp_, compute_);
+  launches_ += len ? 1 : 0;
+  rt_d2h(h_tmp_, d_tmp_, sizeof(unsigned long long), compute_);
+  rt_d2h(h_tmp_ + 32, st.carry[st.cur], sizeof(KpcStreamCarry), compute_);
+  rt_stream_sync(compute_);
+  KpcStreamCarry c;
+  memcpy(&c, h_tmp_ + 32, sizeof c);
+  st.total_lines = c.s1.count + h_tmp_[0];
+  uint64_t recs = st.total_lines / 4;
+  if (st.tail_unsafe && (st.total_lines % 4) != 0)
+    throw KpcError(KPC_E_UNSUPPORTED,
+                   "truncated FASTQ whose last lines are longer than the staging size (raise KPC_CHUNK_BYTES)");
+  st.records = recs;
+  return recs * 4;
+}
+
+void KpcEngine::run_launch(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch) {
+  uint64_t max_lines = ~0ull;
+  if (format_ != KPC_FASTA) {
+    if (final_launch) max_lines = final_line_cap(st, dev, len);
+    if (pair_limit_ >= 0) max_lines = std::min<uint64_t>(max_lines, (uint64_t)pair_limit_ * 4);
+  }
+  switch (mode_) {
+    case DENSE: {
+      KpcDenseSink ds{dense_lo_};
+      (void)ds;
+      launch_tiles(st, mate, dev, len, final_launch, max_lines, KPC_SINK_DENSE, nullptr, nullptr, false, nullptr, 0);
+      advance(st, len);
+      dense_after_launch(len);
+      break;
+    }
+    case HASH: hash_process(st, mate, dev, len, final_launch, max_lines); break;
+    case TUPLE: tuple_process(st, mate, dev, len, final_launch, max_lines); break;
+  }
+}
+
+void KpcEngine::launch_tiles(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch,
+                             uint64_t max_lines, int sink_kind, const KpcHashSink *hs, const KpcTupleSink *ts,
+                             bool with_recs, unsigned long long *probe_pos, uint64_t probe_from) {
+  const uint64_t n_tiles = (len + tile_bytes_ - 1) / tile_bytes_;
+  if (n_tiles == 0) {
+    // nothing to scan: the state simply carries over
+    rt_d2d(st.carry[st.cur ^ 1], st.carry[st.cur], sizeof(KpcStreamCarry), compute_);
+    return;
+  }
+  if (n_tiles >= 0xffffffffull) throw KpcError(KPC_E_UNSUPPORTED, "launch too large");
+  ensure_desc(n_tiles);
+  ++epoch_;
+  if (epoch_ >= (1u << 30)) {  // flags hold epoch << 2
+    rt_memset(desc_, 0, desc_cap_ * sizeof(KpcTileDesc), compute_);
+    epoch_ = 1;
+  }
+  rt_memset(tile_counter_, 0, sizeof(uint32_t), compute_);
+  KpcTileLaunch L;
+  memset(&L, 0, sizeof L);
+  L.fmt = format_ == KPC_FASTA ? KPC_FMT_FASTA : KPC_FMT_FASTQ;
+  L.content = cfg_.content;
+  L.sink = sink_kind;
+  L.p.data = dev;
+  L.p.n = len;
+  L.p.abs_base = st.fed;
+  L.p.rank_base = rank_base_;
+  L.p.rank_mates = format_ == KPC_FASTQ_PE ? 2 : 1;
+  L.p.rank_mate = (uint32_t)mate;
+  L.p.max_lines = max_lines;
+  L.p.k = cfg_.k;
+  L.p.epoch = epoch_;
+  L.p.n_tiles = (uint32_t)n_tiles;
+  L.p.final_launch = final_launch ? 1 : 0;
+  L.p.desc = desc_;
+  L.p.carry_in = st.carry[st.cur];
+  L.p.carry_out = st.carry[st.cur ^ 1];
+  L.p.tile_counter = tile_counter_;
+  L.p.err_line = st.err_line;
+  L.p.rec_tab = with_recs ? d_recs_ : nullptr;
+  L.p.probe_pos = probe_pos;
+  L.p.probe_from = probe_from;
+  if (sink_kind == KPC_SINK_DENSE) L.dense.table = dense_lo_;
+  if (hs) L.hash = *hs;
+  if (ts) L.tuple = *ts;
+  L.p.rec_base = tuple_rec_base_;
+  L.p.rec_cap = d_recs_cap_;
+  kpc_k_tiles(L, compute_);
+  ++launches_;
+}
+
+void KpcEngine::advance(StreamState &st, size_t len) {
+  st.fed += len;
+  st.cur ^= 1;
+}
+
+void KpcEngine::end() {
+  if (!in_input_) throw KpcError(KPC_E_STATE, "kpc_end without kpc_begin");
+  const int mates = format_ == KPC_FASTQ_PE ? 2 : 1;
+  for (int m = 0; m < mates; ++m)
+    if (!streams_[m].eof) throw KpcError(KPC_E_STATE, "kpc_end before eof was signalled on every mate");
+  in_input_ = false;
+  rt_stream_sync(copy_);
+  if (format_ != KPC_FASTA) {
+    // Malformed records (Files.ml:213-214, 241-243): only complete records / pairs are ever checked
+    for (int m = 0; m < mates; ++m) rt_d2h(h_tmp_ + m, streams_[m].err_line, sizeof(unsigned long long), compute_);
+    rt_stream_sync(compute_);
+    uint64_t recs = streams_[0].records;
+    if (mates == 2) {
+      const uint64_t r0 = streams_[0].records, r1 = streams_[1].records;
+      recs = std::min(r0, r1);
+      if (pair_limit_ >= 0) recs = std::min<uint64_t>(recs, (uint64_t)pair_limit_);
+      complete_pairs_ = (long long)recs;
+      const uint64_t used0 = pair_limit_ >= 0 ? std::min<uint64_t>(r0, (uint64_t)pair_limit_) : r0;
+      const uint64_t used1 = pair_limit_ >= 0 ? std::min<uint64_t>(r1, (uint64_t)pair_limit_) : r1;
+      if (used0 != used1 && mode_ != TUPLE) {
+        failed_ = true;
+        throw KpcError(KPC_E_PE_MISMATCH, "paired FASTQ files hold different numbers of records (" +
+                                              std::to_string(r0) + " and " + std::to_string(r1) + ")");
+      }
+    }
+    uint64_t bad = ~0ull;
+    for (int m = 0; m < mates; ++m)
+      if (h_tmp_[m] != ~0ull && h_tmp_[m] / 4 < recs) bad = std::min<uint64_t>(bad, h_tmp_[m] / 4);
+    if (mode_ == TUPLE) tuple_flush(true);
+    if (bad != ~0ull) {
+      failed_ = true;
+      throw KpcError(KPC_E_MALFORMED_FASTQ, "On line " + std::to_string((bad + 1) * 4 * mates) + ": Malformed FASTQ file");
+    }
+    rank_base_ += recs * mates;
+  } else {
+    if (mode_ == TUPLE) tuple_flush(true);
+    rank_base_ += streams_[0].fed;
+  }
+}
+
+void KpcEngine::finish() {
+  if (in_input_) throw KpcError(KPC_E_STATE, "kpc_finish inside an input");
+  if (failed_) throw KpcError(KPC_E_STATE, "context is in a failed state");
+  if (!header_done_) return;  // no input at all: the reference prints nothing (bin/KPopCount.ml:218)
+  switch (mode_) {
+    case DENSE: dense_finish(); break;
+    case HASH: hash_finish(); break;
+    case TUPLE: tuple_finish(); break;
+  }
+}
+
+// =================================================================================================
+// DENSE
+// =================================================================================================
+void KpcEngine::dense_after_launch(size_t len) {
+  // every byte yields at most one window: fold the u32 counters before any of them can wrap
+  dense_since_fold_ += len;
+  if (dense_since_fold_ >= (1ull << 31)) {
+    if (!dense_hi_) {
+      dense_hi_ = (unsigned long long *)rt_dmalloc(nbins_ * sizeof(unsigned long long));
+      rt_memset(dense_hi_, 0, nbins_ * sizeof(unsigned long long), compute_);
+    }
+    kpc_k_dense_fold(dense_lo_, dense_hi_, nbins_, compute_);
+    ++launches_;
+    dense_since_fold_ = 0;
+  }
+}
+
+void KpcEngine::dense_finish() {
+  // every key is its own bucket (4^k <= B): Hashtbl.iter order is ascending key order
+  unsigned long long *keys = (unsigned long long *)scratch(nbins_ * 16 + kpc_k_scan_scratch_bytes(nbins_) + 512);
+  unsigned long long *counts = keys + nbins_;
+  void *scan = counts + nbins_;
+  kpc_k_dense_extract(dense_lo_, dense_hi_, nbins_, keys, counts, d_tmp_ + 4, scan, compute_);
+  launches_ += 3;
+  rt_d2h(h_tmp_ + 4, d_tmp_ + 4, sizeof(unsigned long long), compute_);
+  rt_stream_sync(compute_);
+  emit_entries(keys, counts, h_tmp_[4]);
+}
+
+unsigned long long KpcEngine::kmers_counted() {
+  if (mode_ != DENSE) throw KpcError(KPC_E_UNSUPPORTED, "kpc_kmers_counted is only available on the dense-table path");
+  // sum of the table == sum of all emitted counts
+  unsigned long long *keys = (unsigned long long *)scratch(nbins_ * 16 + kpc_k_scan_scratch_bytes(nbins_) + 512);
+  unsigned long long *counts = keys + nbins_;
+  void *scan = counts + nbins_;
+  kpc_k_dense_extract(dense_lo_, dense_hi_, nbins_, keys, counts, d_tmp_ + 4, scan, compute_);
+  rt_d2h(h_tmp_ + 4, d_tmp_ + 4, sizeof(unsigned long long), compute_);
+  rt_stream_sync(compute_);
+  const uint64_t n = h_tmp_[4];
+  std::vector<unsigned long long> hc(n);
+  if (n) rt_d2h(hc.data(), counts, n * 8, compute_);
+  rt_stream_sync(compute_);
+  unsigned long long s = 0;
+  for (uint64_t i = 0; i < n; ++i) s += hc[i];
+  return s;
+}
+
+void KpcEngine::dense_table(void **lo, void **hi, unsigned long long *nbins) {
+  if (mode_ != DENSE) throw KpcError(KPC_E_STATE, "not on the dense-table path");
+  rt_stream_sync(compute_);
+  *lo = dense_lo_;
+  *hi = dense_hi_;
+  *nbins = nbins_;
+}
+unsigned long long KpcEngine::dense_max() {
+  if (mode_ != DENSE) throw KpcError(KPC_E_STATE, "not on the dense-table path");
+  rt_memset(d_tmp_ + 5, 0, 8, compute_);
+  kpc_k_dense_max(dense_lo_, dense_hi_, nbins_, d_tmp_ + 5, compute_);
+  ++launches_;
+  rt_d2h(h_tmp_ + 5, d_tmp_ + 5, 8, compute_);
+  rt_stream_sync(compute_);
+  return h_tmp_[5];
+}
+void KpcEngine::dense_promote() {
+  if (mode_ != DENSE) throw KpcError(KPC_E_STATE, "not on the dense-table path");
+  if (!dense_hi_) {
+    dense_hi_ = (unsigned long long *)rt_dmalloc(nbins_ * sizeof(unsigned long long));
+    rt_memset(dense_hi_, 0, nbins_ * sizeof(unsigned long long), compute_);
+  }
+  kpc_k_dense_promote(dense_lo_, dense_hi_, nbins_, compute_);
+  ++launches_;
+  dense_since_fold_ = 0;
+  rt_stream_sync(compute_);
+}
+
+void KpcEngine::synth_fastq(void *dev_out, unsigned long long first, unsigned long long n, unsigned long long seed) {
+  kpc_k_synth_fastq((uint8_t *)dev_out, first, n, seed, compute_);
+  rt_stream_sync(compute_);
+}
+
+// =================================================================================================
+// HASH  (k > 12, DNA-ss k = 12, protein k > 4, or a small -M): table + insertion ranks + spill epochs
+// =================================================================================================
+void KpcEngine::hash_init() {
+  d_hstat_ = (unsigned long long *)rt_dmalloc(2 * sizeof(unsigned long long));
+  rt_memset(d_hstat_, 0, 2 * sizeof(unsigned long long), compute_);
+  hcap_ = 0;
+  hdistinct_ = 0;
+}
+
+KpcHashSink KpcEngine::hash_sink(uint64_t lo, uint64_t hi, long long sign) const {
+  KpcHashSink h;
+  h.keys = hkeys_; h.counts = hcounts_; h.ranks = hranks_;
+  h.n_new = d_hstat_; h.overflow = d_hstat_ + 1;
+  h.mask = hcap_ - 1;
+  h.rank_lo = lo; h.rank_hi = hi; h.sign = sign;
+  return h;
+}
+
+// room for `need` distinct keys at a load factor <= 1/2
+void KpcEngine::hash_ensure_capacity(uint64_t need) {
+  uint64_t want = pow2_at_least(1024, need * 2);
+  if (want <= hcap_) return;
+  unsigned long long *ok = hkeys_, *oc = hcounts_, *orr = hranks_;
+  const uint64_t ocap = hcap_;
+  hkeys_ = (unsigned long long *)rt_dmalloc(want * 8);
+  hcounts_ = (unsigned long long *)rt_dmalloc(want * 8);
+  hranks_ = (unsigned long long *)rt_dmalloc(want * 8);
+  hcap_ = want;
+  kpc_k_hash_clear(hkeys_, hcounts_, hranks_, hcap_, compute_);
+  ++launches_;
+  if (ocap) {
+    rt_memset(d_hstat_, 0, 2 * sizeof(unsigned long long), compute_);
+    KpcHashSink nw = hash_sink(0, ~0ull, 1);
+    kpc_k_hash_rehash(ok, oc, orr, ocap, nw, compute_);
+    ++launches_;
+    rt_stream_sync(compute_);
+    rt_dfree(ok); rt_dfree(oc); rt_dfree(orr);
+  }
+}
+
+// dump in Hashtbl.iter order, then (optionally) Hashtbl.clear
+void KpcEngine::hash_dump(bool clear) {
+  if (hcap_) {
+    const size_t need = hcap_ ? (size_t)std::min<uint64_t>(hcap_, hdistinct_ + 1) : 1;
+    unsigned long long *ok = (unsigned long long *)scratch(need * 24 + kpc_k_scan_scratch_bytes(hcap_) + 1024);
+    unsigned long long *oc = ok + need, *orr = oc + need;
+    void *scan = orr + need;
+    kpc_k_hash_extract(hkeys_, hcounts_, hranks_, hcap_, ok, oc, orr, d_tmp_ + 6, scan, compute_);
+    launches_ += 3;
+    rt_d2h(h_tmp_ + 6, d_tmp_ + 6, 8, compute_);
+    rt_stream_sync(compute_);
+    const uint64_t n = h_tmp_[6];
+    const uint64_t B = grow_buckets(n);
+    if (n) {
+      void *os = scratch2(kpc_k_order_scratch_bytes(n));
+      kpc_k_order_entries(ok, oc, orr, nullptr, n, B - 1, nullptr, 0, os, compute_);
+      launches_ += 8;
+      rt_stream_sync(compute_);
+      emit_entries(ok, oc, n);
+    }
+    if (clear) {
+      kpc_k_hash_clear(hkeys_, hcounts_, hranks_, hcap_, compute_);
+      ++launches_;
+      rt_memset(d_hstat_, 0, 2 * sizeof(unsigned long long), compute_);
+      hdistinct_ = 0;
+    }
+  }
+}
+
+void KpcEngine::hash_process(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch,
+                             uint64_t max_lines) {
+  const uint64_t M = (uint64_t)cfg_.max_results_size;
+  hash_ensure_capacity(hdistinct_ + len + 16);
+  uint64_t lo = epoch_rank_lo_;
+  uint64_t hi = ~0ull;
+  auto run = [&](uint64_t rlo, uint64_t rhi, long long sign) {
+    KpcHashSink h = hash_sink(rlo, rhi, sign);
+    launch_tiles(st, mate, dev, len, final_launch, max_lines, KPC_SINK_HASH, &h, nullptr, false, nullptr, 0);
+    rt_d2h(h_tmp_, d_hstat_, 2 * sizeof(unsigned long long), compute_);
+    rt_d2h(h_tmp_ + 2, st.err_line, sizeof(unsigned long long), compute_);
+    rt_stream_sync(compute_);
+    if (h_tmp_[1]) throw KpcError(KPC_E_NOMEM, "internal: hash table overflow");
+    hdistinct_ = h_tmp_[0];
+  };
+  run(lo, hi, 1);
+  // a malformed FASTQ record ends the run there: nothing from that record on may influence the spill dumps
+  if (format_ != KPC_FASTA && h_tmp_[2] != ~0ull && pair_limit_ < 0) {
+    const uint64_t bad_rec = h_tmp_[2] / 4;
+    const uint64_t mates = format_ == KPC_FASTQ_PE ? 2 : 1;
+    const uint64_t stop = (rank_base_ + bad_rec * mates) << 32;
+    run(stop, ~0ull, -1);
+    hi = stop;
+  }
+  // the dump/clear rule of bin/KPopCount.ml:39: after a record, if length res >= M
+  while (hdistinct_ >= M) {
+    // rank of the M-th distinct key of this epoch: the record that holds it is where the table reaches M
+    const size_t need = (size_t)hdistinct_ + 1;
+    unsigned long long *ok = (unsigned long long *)scratch(need * 24 + kpc_k_scan_scratch_bytes(hcap_) + 1024);
+    unsigned long long *oc = ok + need, *orr = oc + need;
+    void *scan = orr + need;
+    kpc_k_hash_extract(hkeys_, hcounts_, hranks_, hcap_, ok, oc, orr, d_tmp_ + 6, scan, compute_);
+    launches_ += 3;
+    rt_d2h(h_tmp_ + 6, d_tmp_ + 6, 8, compute_);
+    rt_stream_sync(compute_);
+    const uint64_t n = h_tmp_[6];
+    if (n < M) break;
+    std::vector<unsigned long long> ranks(n);
+    rt_d2h(ranks.data(), orr, n * 8, compute_);
+    rt_stream_sync(compute_);
+    std::nth_element(ranks.begin(), ranks.begin() + (M - 1), ranks.end());
+    const uint64_t rstar = ranks[M - 1];
+    // first rank of the record after the one that holds rstar
+    uint64_t next_rec_rank = ~0ull;
+    if (format_ != KPC_FASTA) {
+      next_rec_rank = ((rstar >> 32) + 1) << 32;
+      // is there anything at or after it in what has been fed?  (windows of later launches have larger ranks)
+    } else {
+      rt_memset(d_tmp_ + 7, 0xff, 8, compute_);
+      const uint64_t from = rstar - rank_base_ + 1;  // stream offset just after the window's last symbol
+      launch_tiles(st, mate, dev, len, final_launch, max_lines, KPC_SINK_NULL, nullptr, nullptr, false, d_tmp_ + 7, from);
+      rt_d2h(h_tmp_ + 7, d_tmp_ + 7, 8, compute_);
+      rt_stream_sync(compute_);
+      if (h_tmp_[7] != ~0ull) next_rec_rank = rank_base_ + h_tmp_[7];
+    }
+    bool record_ends_here;
+    if (format_ != KPC_FASTA) {
+      // Two mate files are scanned independently here, so the point in the pair order where the table reaches M
+      // cannot be reconstructed launch by launch: refuse rather than print a dump at the wrong record.
+      if (format_ == KPC_FASTQ_PE)
+        throw KpcError(KPC_E_UNSUPPORTED, "paired-end input whose table reaches -M on the hash path");
+      // the record of rstar is over once the line feed of its sequence line has been seen
+      rt_d2h(h_tmp_ + 32, st.carry[st.cur ^ 1], sizeof(KpcStreamCarry), compute_);
+      rt_stream_sync(compute_);
+      KpcStreamCarry co;
+      memcpy(&co, h_tmp_ + 32, sizeof co);
+      const uint64_t jstar = (rstar >> 32) - rank_base_;
+      record_ends_here = final_launch || co.s1.count >= 4 * jstar + 2;
+    } else {
+      record_ends_here = next_rec_rank != ~0ull || final_launch;
+    }
+    if (!record_ends_here) break;  // the record continues in the next launch: decide there
+    if (next_rec_rank < hi) {
+      // take back everything from the next record on, dump, clear, and count it again into the fresh table
+      run(next_rec_rank, hi, -1);
+      hdistinct_ = n;  // entries that fell to zero are not printed; size for the bucket growth is recomputed in dump
+      hash_dump(true);
+      epoch_rank_lo_ = next_rec_rank;
+      run(next_rec_rank, hi, 1);
+    } else {
+      hash_dump(true);  // nothing from a later record has been counted yet
+      break;
+    }
+  }
+  advance(st, len);
+}
+
+void KpcEngine::hash_finish() { hash_dump(false); }
+
+// =================================================================================================
+// TUPLE  (-L: one spectrum per record).  Synchronous per launch: this is not the throughput path.
+// =================================================================================================
+void KpcEngine::tuple_process(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch,
+                              uint64_t max_lines) {
+  const int mates = format_ == KPC_FASTQ_PE ? 2 : 1;
+  // room for one tuple per byte on top of what is buffered
+  if (tn_ + len + 16 > tcap_) {
+    uint64_t ncap = std::max<uint64_t>(tn_ + len + 16, tcap_ * 2);
+    unsigned long long *nk = (unsigned long long *)rt_dmalloc(ncap * 8);
+    unsigned long long *nr = (unsigned long long *)rt_dmalloc(ncap * 8);
+    uint32_t *nc = (uint32_t *)rt_dmalloc(ncap * 4);
+    if (tn_) {
+      rt_d2d(nk, tkeys_, tn_ * 8, compute_);
+      rt_d2d(nr, tranks_, tn_ * 8, compute_);
+      rt_d2d(nc, trecs_, tn_ * 4, compute_);
+    }
+    rt_stream_sync(compute_);
+    rt_dfree(tkeys_); rt_dfree(tranks_); rt_dfree(trecs_);
+    tkeys_ = nk; tranks_ = nr; trecs_ = nc; tcap_ = ncap;
+  }
+  // records that can show up in this launch start with the one that is open when it begins
+  rt_d2h(h_tmp_ + 32, st.carry[st.cur], sizeof(KpcStreamCarry), compute_);
+  rt_stream_sync(compute_);
+  KpcStreamCarry cin;
+  memcpy(&cin, h_tmp_ + 32, sizeof cin);
+  const uint64_t rec_base = format_ == KPC_FASTA ? (cin.s1.count ? cin.s1.count - 1 : 0) : (cin.s1.count >> 2);
+  const uint64_t rec_cap = len / 2 + 4;
+  if (rec_cap > d_recs_cap_) {
+    rt_dfree(d_recs_);
+    d_recs_cap_ = rec_cap + rec_cap / 4;
+    d_recs_ = (KpcRecEntry *)rt_dmalloc(d_recs_cap_ * sizeof(KpcRecEntry));
+  }
+  rt_memset(d_recs_, 0xff, d_recs_cap_ * sizeof(KpcRecEntry), compute_);
+  KpcTupleSink ts;
+  ts.keys = tkeys_; ts.ranks = tranks_; ts.recs = trecs_; ts.n_out = d_tn_; ts.cap = tcap_;
+  ts.mates = (uint32_t)mates; ts.mate = (uint32_t)mate;
+  tuple_rec_base_ = rec_base;
+  launch_tiles(st, mate, dev, len, final_launch, max_lines, KPC_SINK_TUPLE, nullptr, &ts, true, nullptr, 0);
+  rt_d2h(h_tmp_ + 32, st.carry[st.cur ^ 1], sizeof(KpcStreamCarry), compute_);
+  rt_d2h(h_tmp_, d_tn_, 8, compute_);
+  rt_stream_sync(compute_);
+  KpcStreamCarry cout;
+  memcpy(&cout, h_tmp_ + 32, sizeof cout);
+  tn_ = h_tmp_[0];
+  if (tn_ > tcap_) throw KpcError(KPC_E_NOMEM, "internal: tuple buffer overflow");
+  // ---- record names: cut out of the host copy of this launch ----
+  const uint64_t rec_end = format_ == KPC_FASTA ? cout.s1.count : (cout.s1.count >> 2) + 1;
+  const uint64_t nrec = std::min<uint64_t>(rec_end > rec_base ? rec_end - rec_base : 0, d_recs_cap_);
+  std::vector<KpcRecEntry> ent(nrec);
+  if (nrec) {
+    rt_d2h(ent.data(), d_recs_, nrec * sizeof(KpcRecEntry), compute_);
+    rt_stream_sync(compute_);
+  }
+  std::vector<RecInfo> &open = open_recs_[mate];
+  const uint64_t l0 = st.fed, l1 = st.fed + len;
+  for (uint64_t j = 0; j < nrec; ++j) {
+    const uint64_t r = rec_base + j;
+    if (r < rec_done_[mate]) continue;
+    const size_t idx = (size_t)(r - rec_done_[mate]);
+    const bool starts = ent[j].tag_start != ~0ull;
+    const bool known = idx < open.size() && open[idx].have_tag;
+    if (!starts && !known) continue;
+    if (idx >= open.size()) open.resize(idx + 1);
+    RecInfo &ri = open[idx];
+    uint64_t a = ~0ull, b = ~0ull;
+    if (starts) { ri.tag_start = ent[j].tag_start; ri.have_tag = true; a = ent[j].tag_start; }
+    else if (ri.tag_end == ~0ull) a = l0;  // a name that began in an earlier launch goes on
+    if (a != ~0ull) {
+      if (ent[j].tag_end != ~0ull) { ri.tag_end = ent[j].tag_end; b = ent[j].tag_end; }
+      else b = l1;
+      if (b > a) ri.tag.append((const char *)tag_bytes_.data() + (a - l0), (size_t)(b - a));
+    }
+  }
+  advance(st, len);
+  // ---- how far this mate's records are final ----
+  if (format_ == KPC_FASTA) {
+    st.records = cout.s1.count;
+    st.final_recs = final_launch ? cout.s1.count : (cout.s1.count ? cout.s1.count - 1 : 0);
+  } else {
+    // all four lines seen (and, by the hold-back rule of choose_cut, the record is complete)
+    st.final_recs = final_launch ? st.records : (cout.s1.count >> 2);
+  }
+  tuple_flush(false);
+}
+
+// write out every record that is final on all mates of the current input
+void KpcEngine::tuple_flush(bool input_done) {
+  const int mates = format_ == KPC_FASTQ_PE ? 2 : 1;
+  uint64_t fin[2] = {streams_[0].final_recs, mates == 2 ? streams_[1].final_recs : 0};
+  if (format_ != KPC_FASTA) {
+    // never go past the first malformed record / pair (Files.ml:213-214, 241-243)
+    for (int m = 0; m < mates; ++m) rt_d2h(h_tmp_ + m, streams_[m].err_line, 8, compute_);
+    rt_stream_sync(compute_);
+    uint64_t bad = ~0ull;
+    for (int m = 0; m < mates; ++m)
+      if (h_tmp_[m] != ~0ull) bad = std::min<uint64_t>(bad, h_tmp_[m] / 4);
+    if (input_done && mates == 2) {  // FASTQ.iter_pe stops at the shorter file
+      const uint64_t pairs = std::min(streams_[0].records, streams_[1].records);
+      fin[0] = std::min(fin[0], pairs);
+      fin[1] = std::min(fin[1], pairs);
+    }
+    for (int m = 0; m < mates; ++m) fin[m] = std::min(fin[m], bad);
+  }
+  // positions in iteration order interleave the mates: g = record * mates + mate.  A pair is only visited when
+  // both of its records are complete (FASTQ.iter_pe reads all eight lines first, Files.ml:228-239).
+  const uint64_t g_hi = mates == 2 ? 2 * std::min(fin[0], fin[1]) : fin[0];
+  const uint64_t g_lo = mates == 2 ? 2 * rec_done_[0] : rec_done_[0];
+  if (g_hi <= g_lo) return;
+  if (g_hi >= 0xffffffffull) throw KpcError(KPC_E_UNSUPPORTED, "more than 2^32 records in one -L input");
+  const uint64_t nrec = g_hi - g_lo;
+  // ---- reduce the buffered tuples: sort by (record, key), run-length ----
+  uint64_t n_final = 0, keep_from = tn_;
+  unsigned long long *ek = nullptr, *ec = nullptr, *er = nullptr;
+  uint32_t *erec = nullptr;
+  std::vector<unsigned long long> per_rec(nrec, 0);  // distinct k-mers of every record in [g_lo, g_hi)
+  if (tn_) {
+    const size_t n = (size_t)tn_;
+    char *base = (char *)scratch(n * 28 + 4096);
+    ek = (unsigned long long *)base;
+    ec = ek + n;
+    er = ec + n;
+    erec = (uint32_t *)(er + n);
+    void *os = scratch2(kpc_k_order_scratch_bytes(n));
+    kpc_k_tuple_reduce(tkeys_, tranks_, trecs_, n, ek, ec, er, erec, d_tmp_ + 6, os, compute_);
+    launches_ += 10;
+    rt_d2h(h_tmp_ + 6, d_tmp_ + 6, 8, compute_);
+    rt_stream_sync(compute_);
+    const uint64_t n_entries = h_tmp_[6];
+    // the tuple arrays are now sorted by record: those of records >= g_hi stay buffered
+    std::vector<uint32_t> hrecs(n);
+    rt_d2h(hrecs.data(), trecs_, n * 4, compute_);
+    std::vector<uint32_t> hrec_e(n_entries);
+    if (n_entries) rt_d2h(hrec_e.data(), erec, n_entries * 4, compute_);
+    rt_stream_sync(compute_);
+    keep_from = (uint64_t)(std::lower_bound(hrecs.begin(), hrecs.end(), (uint32_t)g_hi) - hrecs.begin());
+    n_final = (uint64_t)(std::lower_bound(hrec_e.begin(), hrec_e.end(), (uint32_t)g_hi) - hrec_e.begin());
+    for (uint64_t i = 0; i < n_final; ++i)
+      if (hrec_e[i] >= g_lo) per_rec[hrec_e[i] - g_lo]++;
+  }
+  // ---- order inside each record: Hashtbl.iter with the bucket count the table has at that point ----
+  const int bits = sbits_ * cfg_.k;
+  std::vector<unsigned long long> bmask(nrec);
+  bool grew = false;
+  bool identity_order = true;
+  for (uint64_t j = 0; j < nrec; ++j) {
+    const uint64_t before = buckets_;
+    grow_buckets(per_rec[j]);
+    if (buckets_ != before) grew = true;
+    bmask[j] = buckets_ - 1;
+    if (bits >= 64 || (1ull << bits) > buckets_) identity_order = false;
+  }
+  if (bits < 64 && (1ull << bits) <= bmask[0] + 1) identity_order = true;  // B only grows
+  if (n_final && !identity_order) {
+    const size_t ob = (kpc_k_order_scratch_bytes(n_final) + 255) & ~(size_t)255;
+    char *os = (char *)scratch2(ob + nrec * 8 + 256);
+    unsigned long long *d_bmask = nullptr;
+    if (grew) {
+      d_bmask = (unsigned long long *)(os + ob);
+      rt_h2d(d_bmask, bmask.data(), nrec * 8, compute_);
+    }
+    kpc_k_order_entries(ek, ec, er, erec, n_final, buckets_ - 1, d_bmask, (uint32_t)g_lo, os, compute_);
+    launches_ += 10;
+    rt_stream_sync(compute_);
+  }
+  // ---- text of all entries, then cut per record and put the header lines in between ----
+  std::vector<char> lines;
+  {
+    struct Collect {
+      static int fn(void *u, const char *b, size_t n) {
+        std::vector<char> *v = (std::vector<char> *)u;
+        v->insert(v->end(), b, b + n);
+        return 0;
+      }
+    };
+    kpc_sink_fn saved = sink_;
+    void *saved_user = sink_user_;
+    sink_ = Collect::fn;
+    sink_user_ = &lines;
+    try {
+      emit_entries(ek, ec, n_final);
+    } catch (...) {
+      sink_ = saved; sink_user_ = saved_user;
+      throw;
+    }
+    sink_ = saved;
+    sink_user_ = saved_user;
+  }
+  size_t lp = 0;
+  bool quotes_error = false;
+  std::string bad_tag, text;
+  for (uint64_t j = 0; j < nrec; ++j) {
+    const uint64_t g = g_lo + j;
+    const int m = (int)(g % mates);
+    const uint64_t r = g / mates;
+    const std::vector<RecInfo> &open = open_recs_[m];
+    const size_t idx = (size_t)(r - rec_done_[m]);
+    const std::string tag = idx < open.size() ? open[idx].tag : std::string();
+    size_t lend = lp;
+    for (unsigned long long c = 0; c < per_rec[j]; ++c) {
+      const char *q = (const char *)memchr(lines.data() + lend, '\n', lines.size() - lend);
+      lend = (size_t)(q - lines.data()) + 1;
+    }
+    const bool skip = format_ == KPC_FASTA && tag.empty();  // Files.ml:101-106: records without a name are dropped
+    if (!skip) {
+      std::string clean;
+      if (!strip_quotes(tag, clean)) { quotes_error = true; bad_tag = tag; break; }  // bin/KPopCount.ml:45
+      text.assign("\t");
+      text += clean;
+      text += "\n";
+      emit(text.data(), text.size());
+      emit(lines.data() + lp, lend - lp);
+    }
+    lp = lend;
+  }
+  // ---- forget what has been written ----
+  for (int m = 0; m < mates; ++m) {
+    const uint64_t new_done = mates == 2 ? g_hi / 2 : g_hi;
+    std::vector<RecInfo> &open = open_recs_[m];
+    const size_t drop = (size_t)std::min<uint64_t>(new_done - rec_done_[m], open.size());
+    open.erase(open.begin(), open.begin() + drop);
+    rec_done_[m] = new_done;
+  }
+  if (tn_) {
+    const uint64_t left = tn_ - keep_from;
+    if (left && keep_from) {  // (source and destination may overlap: go through a scratch buffer)
+      char *tmp = (char *)scratch2((size_t)left * 8 + 256);
+      rt_d2d(tmp, tkeys_ + keep_from, left * 8, compute_);  rt_d2d(tkeys_, tmp, left * 8, compute_);
+      rt_d2d(tmp, tranks_ + keep_from, left * 8, compute_); rt_d2d(tranks_, tmp, left * 8, compute_);
+      rt_d2d(tmp, trecs_ + keep_from, left * 4, compute_);  rt_d2d(trecs_, tmp, left * 4, compute_);
+    }
+    tn_ = left;
+    h_tmp_[0] = tn_;
+    rt_h2d(d_tn_, h_tmp_, 8, compute_);
+    rt_stream_sync(compute_);
+  }
+  if (quotes_error) {
+    failed_ = true;
+    throw KpcError(KPC_E_QUOTES_IN_NAME, "Quotes_in_name(\"" + bad_tag + "\")");
+  }
+}
+
+void KpcEngine::tuple_finish() {
+  // every record was written when it completed; the final KIHF.iter finds an empty table (bin/KPopCount.ml:49,60)
+}

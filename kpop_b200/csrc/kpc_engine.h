@@ -1,0 +1,191 @@
+// kpc_engine.h -- host side of libkpopcount_gpu: the state machine behind the C ABI (include/kpopcount.h).
+//
+// It restates KMerCounter.compute (bin/KPopCount.ml:26-63) around the device kernels:
+//   * cuts the incoming byte stream of every input into launches (line aligned when possible), keeping back
+//     the last lines of a FASTQ stream so that the "EOF inside a record drops it" rule of FASTQ.iter_se
+//     (Files.ml:217) can be applied exactly,
+//   * picks the table for the run:  DENSE  4^k / 32^k u32 bins when every key is its own OCaml bucket and the
+//     table can never reach -M (default parameters, k <= 12);  HASH  open addressing + insertion ranks, with
+//     the dump/clear rule of bin/KPopCount.ml:39 reproduced epoch by epoch;  TUPLE  for -L (one spectrum per
+//     record): (record, key) tuples reduced by sort + run-length,
+//   * orders and formats the dump on the device and hands the text to the sink.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/kpopcount.h"
+#include "kpc_kernels.h"
+
+struct KpcEngineConfig {
+  int k = 12;
+  int content = KPC_DNA_DS;
+  long long max_results_size = 16777216;
+  std::string label;
+  int device = 0;
+};
+
+class KpcEngine {
+ public:
+  explicit KpcEngine(const KpcEngineConfig &cfg);
+  ~KpcEngine();
+
+  void set_sink(kpc_sink_fn fn, void *user) { sink_ = fn; sink_user_ = user; }
+  int staging_slots() const { return kStagingSlots; }
+  void *staging(int slot, size_t *capacity);
+  void begin(int format);
+  void feed(int mate, const uint8_t *bytes, size_t n, bool eof);
+  void feed_device(int mate, const uint8_t *dev, size_t n, bool eof);
+  void set_pair_limit(long long n) { pair_limit_ = n; }
+  long long complete_pairs() const { return complete_pairs_; }
+  void end();
+  void finish();
+  unsigned long long kmers_counted();
+  void dense_table(void **lo, void **hi, unsigned long long *nbins);
+  unsigned long long dense_max();
+  void dense_promote();
+  void *native_stream() { return rt_stream_native(compute_); }
+  void sync();
+  unsigned long long launches() const { return launches_; }
+  void synth_fastq(void *dev_out, unsigned long long first, unsigned long long n, unsigned long long seed);
+
+  enum Mode { DENSE, HASH, TUPLE };
+  Mode mode() const { return mode_; }
+
+ private:
+  static const int kStagingSlots = 3;
+  static const int kRing = 3;
+
+  struct Piece {
+    const uint8_t *p;
+    size_t n;
+  };
+  struct StreamState {  // one per mate of the current input
+    uint64_t fed = 0;   // bytes handed to the device so far == stream offset of the next launch
+    uint8_t *hold[2] = {nullptr, nullptr};  // pinned; kept-back tail of the stream (ping-pong: one may be in flight)
+    size_t hold_cap[2] = {0, 0};
+    size_t hold_len = 0;
+    int hold_cur = 0;
+    rt_event hold_ev[2] = {nullptr, nullptr};
+    bool hold_busy[2] = {false, false};
+    KpcStreamCarry *carry[2] = {nullptr, nullptr};  // device; [cur] is the state at offset `fed`
+    int cur = 0;
+    unsigned long long *err_line = nullptr;  // device
+    bool eof = false;
+    bool any = false;
+    uint8_t last_byte = '\n';
+    bool tail_unsafe = false;
+    uint64_t total_lines = 0;
+    uint64_t records = 0;     // FASTQ: complete records (known at end of file); FASTA: header lines
+    uint64_t final_recs = 0;  // -L: records of this mate that can be written out
+  };
+  struct RingSlot {
+    uint8_t *buf = nullptr;
+    rt_event computed = nullptr;
+    bool used = false;
+  };
+
+  // --- stream cutting ---
+  void reset_stream(StreamState &st);
+  void hold_append(StreamState &st, const uint8_t *p, size_t n);
+  size_t choose_cut(StreamState &st, const Piece *pc, int npc, size_t limit);
+  void submit_host(StreamState &st, int mate, const Piece *pc, int npc, size_t len, bool final_launch, bool foreign);
+  void run_launch(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch);
+  uint64_t final_line_cap(StreamState &st, const uint8_t *dev, size_t len);
+  RingSlot &next_slot();
+
+  // --- kernels ---
+  void launch_tiles(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch, uint64_t max_lines,
+                    int sink_kind, const KpcHashSink *hs, const KpcTupleSink *ts, bool with_recs,
+                    unsigned long long *probe_pos, uint64_t probe_from);
+  void advance(StreamState &st, size_t len);
+  void ensure_desc(uint64_t n_tiles);
+
+  // --- mode specific ---
+  void dense_after_launch(size_t len);
+  void dense_finish();
+  void hash_init();
+  void hash_process(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch, uint64_t max_lines);
+  void hash_ensure_capacity(uint64_t need);
+  void hash_dump(bool clear);
+  void hash_finish();
+  void tuple_process(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch, uint64_t max_lines);
+  void tuple_flush(bool input_done);
+  void tuple_finish();
+  KpcHashSink hash_sink(uint64_t lo, uint64_t hi, long long sign) const;
+
+  // --- output ---
+  void emit(const char *p, size_t n);
+  void emit_entries(unsigned long long *keys, unsigned long long *counts, uint64_t n);
+  void *scratch(size_t bytes);
+  void *scratch2(size_t bytes);
+  uint64_t grow_buckets(uint64_t size_reached);
+
+  KpcEngineConfig cfg_;
+  Mode mode_;
+  int sbits_, hex_width_;
+  uint64_t nbins_ = 0;
+  uint64_t buckets_;  // current OCaml bucket count B (power of two, never shrinks)
+  kpc_sink_fn sink_ = nullptr;
+  void *sink_user_ = nullptr;
+  bool header_done_ = false;
+  bool failed_ = false;
+  int format_ = -1;
+  bool in_input_ = false;
+  long long pair_limit_ = -1;
+  long long complete_pairs_ = -1;
+  uint64_t rank_base_ = 0;    // FASTA: bytes of all previous inputs; FASTQ: records of all previous inputs
+  unsigned long long launches_ = 0;
+
+  rt_stream compute_ = nullptr, copy_ = nullptr;
+  size_t chunk_cap_;
+  uint32_t tile_bytes_;
+  RingSlot ring_[kRing];
+  int ring_next_ = 0;
+  uint8_t *staging_[kStagingSlots] = {nullptr, nullptr, nullptr};
+  rt_event staging_ev_[kStagingSlots] = {nullptr, nullptr, nullptr};
+  bool staging_busy_[kStagingSlots] = {false, false, false};
+  StreamState streams_[2];
+
+  KpcTileDesc *desc_ = nullptr;
+  uint64_t desc_cap_ = 0;
+  uint32_t *tile_counter_ = nullptr;
+  uint32_t epoch_ = 0;
+  unsigned long long *d_tmp_ = nullptr;  // 8 x u64 device scalars
+  unsigned long long *h_tmp_ = nullptr;  // pinned mirror
+  void *scratch_ = nullptr;
+  size_t scratch_cap_ = 0;
+  void *scratch2_ = nullptr;
+  size_t scratch2_cap_ = 0;
+  char *h_out_ = nullptr;  // pinned bounce buffer for text
+  size_t h_out_cap_ = 0;
+
+  // dense
+  uint32_t *dense_lo_ = nullptr;
+  unsigned long long *dense_hi_ = nullptr;
+  uint64_t dense_since_fold_ = 0;
+
+  // hash
+  unsigned long long *hkeys_ = nullptr, *hcounts_ = nullptr, *hranks_ = nullptr;
+  uint64_t hcap_ = 0;
+  unsigned long long *d_hstat_ = nullptr;  // [0] distinct, [1] overflow
+  uint64_t hdistinct_ = 0;
+  uint64_t epoch_rank_lo_ = 0;  // windows with rank < this belong to already dumped epochs
+
+  // tuple (-L)
+  unsigned long long *tkeys_ = nullptr, *tranks_ = nullptr;
+  uint32_t *trecs_ = nullptr;
+  uint64_t tcap_ = 0;
+  unsigned long long *d_tn_ = nullptr;
+  uint64_t tn_ = 0;           // tuples currently buffered (all belong to records >= rec_done_)
+  uint64_t rec_done_[2] = {0, 0};  // per mate: records already written out
+  struct RecInfo {
+    unsigned long long tag_start = ~0ull, tag_end = ~0ull;
+    std::string tag;
+    bool have_tag = false;
+  };
+  std::vector<RecInfo> open_recs_[2];  // records >= rec_done_ whose header has been seen
+  uint64_t tuple_rec_base_ = 0;  // first record index of the name table of the current launch
+  KpcRecEntry *d_recs_ = nullptr;
+  uint64_t d_recs_cap_ = 0;
+  std::vector<uint8_t> tag_bytes_;  // host copy of the bytes of the current launch (record names are cut out of it)
+};
