@@ -100,6 +100,12 @@ int kpc_dense_max(kpc_ctx *ctx, unsigned long long *max_count);
 /* otherwise: hi += lo, lo = 0 on every rank, reduce hi (u64) instead */
 int kpc_dense_promote(kpc_ctx *ctx);
 
+/* empty the tables and forget every input, keeping all allocations (a context can then be used for another run) */
+int kpc_reset(kpc_ctx *ctx);
+/* benchmarking with device-resident input: format the dump on the device but leave the text in HBM */
+int kpc_discard_text(kpc_ctx *ctx, int discard);
+unsigned long long kpc_text_bytes(const kpc_ctx *ctx); /* bytes of spectra text produced since create / reset */
+
 /* ---- instrumentation ---------------------------------------------------------------------------------------- */
 void *kpc_stream(kpc_ctx *ctx);          /* cudaStream_t the counting kernels are launched on */
 int kpc_sync(kpc_ctx *ctx);

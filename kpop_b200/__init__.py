@@ -1,0 +1,16 @@
+"""kpop_b200 -- B200-native back end for KPop's k-mer spectrum counting stage (KPopCount).
+
+The package holds only what that path needs:
+
+* ``csrc/``            hand-written CUDA for sm_100a + the host engine + the C ABI (``include/kpopcount.h``),
+                       built in-tree into ``libkpopcount_gpu.so`` and the ``bin/KPopCount`` executable;
+* ``_native``          ctypes binding of the C ABI (fails loudly when the library or a GPU is missing);
+* ``counter``          ``KMerCounter``: the host-side mirror of the reference's ``KMerCounter.compute`` functor
+                       (bin/KPopCount.ml:20-64) on top of the C ABI;
+* ``distributed``      read-chunk sharding across the GPUs of one box and the NCCL table reduce.
+
+There is no CPU fallback anywhere in this package.
+"""
+from .counter import Content, KMerCounter, KPopCountError, spectra_filename  # noqa: F401
+
+__all__ = ["KMerCounter", "Content", "KPopCountError", "spectra_filename"]

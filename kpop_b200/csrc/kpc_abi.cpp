@@ -85,6 +85,13 @@ const char *kpc_error(const kpc_ctx *ctx) { return ctx ? ctx->error.c_str() : "n
 int kpc_set_sink(kpc_ctx *ctx, kpc_sink_fn sink, void *user) {
   return guarded(ctx, [&](KpcEngine &e) { e.set_sink(sink, user); });
 }
+int kpc_discard_text(kpc_ctx *ctx, int discard) {
+  return guarded(ctx, [&](KpcEngine &e) { e.set_discard_text(discard != 0); });
+}
+unsigned long long kpc_text_bytes(const kpc_ctx *ctx) { return (ctx && ctx->engine) ? ctx->engine->text_bytes() : 0; }
+int kpc_reset(kpc_ctx *ctx) {
+  return guarded(ctx, [&](KpcEngine &e) { e.reset(); });
+}
 int kpc_staging_slots(const kpc_ctx *ctx) { return (ctx && ctx->engine) ? ctx->engine->staging_slots() : 0; }
 void *kpc_staging(kpc_ctx *ctx, int slot, size_t *capacity) {
   void *p = nullptr;

@@ -188,7 +188,7 @@ void *KpcEngine::staging(int slot, size_t *capacity) {
 // output
 // =================================================================================================
 void KpcEngine::emit(const char *p, size_t n) {
-  if (!n) return;
+  if (!n || discard_text_) return;
   if (!sink_) throw KpcError(KPC_E_STATE, "no sink set (kpc_set_sink)");
   if (sink_(sink_user_, p, n) != 0) throw KpcError(KPC_E_IO, "the output sink reported a failure");
 }
@@ -211,6 +211,8 @@ void KpcEngine::emit_entries(unsigned long long *keys, unsigned long long *count
     rt_d2h(h_tmp_ + 8, d_tmp_ + 8, sizeof(unsigned long long), compute_);
     rt_stream_sync(compute_);
     const size_t total = (size_t)h_tmp_[8];
+    text_bytes_ += total;
+    if (discard_text_) continue;  // device-resident benchmarking: the text stays in HBM
     for (size_t o = 0; o < total; o += h_out_cap_) {
       const size_t c = std::min(h_out_cap_, total - o);
       rt_d2h(h_out_, d_text + o, c, compute_);
@@ -243,6 +245,27 @@ void KpcEngine::reset_stream(StreamState &st) {
   rt_h2d(st.carry[1], h_tmp_ + 16, sizeof c, compute_);
   rt_memset(st.err_line, 0xff, sizeof(unsigned long long), compute_);
   rt_stream_sync(compute_);
+}
+
+// back to the state right after construction (tables emptied), keeping every allocation
+void KpcEngine::reset() {
+  if (in_input_) throw KpcError(KPC_E_STATE, "kpc_reset inside an input");
+  rt_stream_sync(copy_);
+  header_done_ = false; failed_ = false; rank_base_ = 0; pair_limit_ = -1; complete_pairs_ = -1;
+  text_bytes_ = 0;
+  buckets_ = pow2_at_least(16, (uint64_t)cfg_.max_results_size);
+  if (mode_ == DENSE) {
+    rt_memset(dense_lo_, 0, nbins_ * sizeof(uint32_t), compute_);
+    if (dense_hi_) rt_memset(dense_hi_, 0, nbins_ * sizeof(unsigned long long), compute_);
+    dense_since_fold_ = 0;
+  } else if (mode_ == HASH) {
+    if (hcap_) { kpc_k_hash_clear(hkeys_, hcounts_, hranks_, hcap_, compute_); ++launches_; }
+    rt_memset(d_hstat_, 0, 2 * sizeof(unsigned long long), compute_);
+    hdistinct_ = 0; epoch_rank_lo_ = 0;
+  } else {
+    tn_ = 0;
+    rt_memset(d_tn_, 0, sizeof(unsigned long long), compute_);
+  }
 }
 
 void KpcEngine::begin(int format) {
@@ -531,6 +554,7 @@ void KpcEngine::launch_tiles(StreamState &st, int mate, const uint8_t *dev, size
   L.fmt = format_ == KPC_FASTA ? KPC_FMT_FASTA : KPC_FMT_FASTQ;
   L.content = cfg_.content;
   L.sink = sink_kind;
+  if (getenv("KPC_DEBUG_NULL_SINK")) L.sink = KPC_SINK_NULL;  // profiling knob: framing + k-mers, no table traffic
   L.p.data = dev;
   L.p.n = len;
   L.p.abs_base = st.fed;

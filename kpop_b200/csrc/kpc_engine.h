@@ -29,7 +29,10 @@ class KpcEngine {
   explicit KpcEngine(const KpcEngineConfig &cfg);
   ~KpcEngine();
 
-  void set_sink(kpc_sink_fn fn, void *user) { sink_ = fn; sink_user_ = user; }
+  void set_sink(kpc_sink_fn fn, void *user) { sink_ = fn; sink_user_ = user; discard_text_ = false; }
+  void set_discard_text(bool d) { discard_text_ = d; }
+  unsigned long long text_bytes() const { return text_bytes_; }
+  void reset();
   int staging_slots() const { return kStagingSlots; }
   void *staging(int slot, size_t *capacity);
   void begin(int format);
@@ -127,6 +130,8 @@ class KpcEngine {
   uint64_t buckets_;  // current OCaml bucket count B (power of two, never shrinks)
   kpc_sink_fn sink_ = nullptr;
   void *sink_user_ = nullptr;
+  bool discard_text_ = false;
+  unsigned long long text_bytes_ = 0;
   bool header_done_ = false;
   bool failed_ = false;
   int format_ = -1;

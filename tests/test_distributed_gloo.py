@@ -1,0 +1,79 @@
+"""world_size = 2 on CPU (gloo): the host logic of the multi-GPU path -- record sharding and the exact table reduce,
+including the switch to a 64-bit reduction when a u32 sum could wrap.  The per-shard tables come from the CPU checker
+(oracle/fast_dense.cpp); on the GPU box the same functions are driven by bench.py with the device tables."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ORACLE_DIR, ROOT
+
+K = 8
+N_REC = 4001
+
+
+def _worker(rank, world, port, tmp, big):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from kpop_b200.distributed import reduce_dense_tables, shard_records
+    from test_oracle_fastdense import SYNTH, dense_table, fastdense
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    first, last = shard_records(N_REC, world, rank)
+    data = subprocess.run([SYNTH, str(first), str(last - first), "3"], stdout=subprocess.PIPE, check=True).stdout
+    lib = fastdense()
+    t = dense_table(lib, data, K, threads=2)
+    if big:  # pretend one bin is close to wrapping on every rank
+        t[5] = np.uint32(0xF0000000)
+    lo = torch.from_numpy(t.view(np.int32).copy())
+
+    def promote():
+        return torch.from_numpy(t.astype(np.int64))
+
+    total = reduce_dense_tables(lo, promote, int(t.max()))
+    if total.dtype == torch.int32:
+        res = total.numpy().view(np.uint32).astype(np.uint64)
+    else:
+        res = total.numpy().astype(np.uint64)
+    np.save(os.path.join(tmp, f"res{rank}_{int(big)}.npy"), res)
+    np.save(os.path.join(tmp, f"dtype{rank}_{int(big)}.npy"), np.array([total.element_size()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("big", [False, True])
+def test_two_rank_shard_and_reduce(tmp_path, big):
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+    from test_oracle_fastdense import SYNTH, dense_table, fastdense
+    port = 29500 + (os.getpid() % 2000) + (1 if big else 0)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), big), nprocs=2, join=True)
+    whole = subprocess.run([SYNTH, "0", str(N_REC), "3"], stdout=subprocess.PIPE, check=True).stdout
+    want = dense_table(fastdense(), whole, K).astype(np.uint64)
+    if big:
+        # what the per-rank tables summed to once bin 5 was overwritten on both ranks
+        from kpop_b200.distributed import shard_records
+        want[5] = 2 * 0xF0000000
+    for r in range(2):
+        got = np.load(tmp_path / f"res{r}_{int(big)}.npy")
+        width = int(np.load(tmp_path / f"dtype{r}_{int(big)}.npy")[0])
+        assert width == (8 if big else 4)
+        assert np.array_equal(got, want)
+
+
+def test_shard_records_tiles_the_range():
+    from kpop_b200.distributed import shard_records
+    for total in (0, 1, 7, 8, 31_781_305):
+        for world in (1, 2, 3, 8):
+            prev = 0
+            for r in range(world):
+                a, b = shard_records(total, world, r)
+                assert a == prev and b >= a
+                prev = b
+            assert prev == total

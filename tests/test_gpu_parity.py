@@ -1,0 +1,245 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (bin/KPopCount is a thin host over it, kpop_b200 the
+ctypes binding), against the oracle on the same inputs -- bit-exact, including emitted order and exit codes.
+Run on a B200 with `pytest -m gpu`."""
+import ctypes
+import gzip
+import hashlib
+import json
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ORACLE_DIR, ROOT, run_cli
+from fuzzgen import fasta, fastq
+from kats import K9, KATS
+from test_emul_fuzz import one_case
+from test_oracle_kats import materialise
+
+pytestmark = pytest.mark.gpu
+
+GPU_BIN = os.path.join(ROOT, "kpop_b200", "bin", "KPopCount")
+SYNTH = os.path.join(ORACLE_DIR, "_build", "synth_fastq")
+
+
+def env_chunk(chunk=None):
+    env = dict(os.environ)
+    if chunk:
+        env["KPC_CHUNK_BYTES"] = str(chunk)
+    return env
+
+
+@pytest.fixture(scope="module")
+def gpu_bin():
+    assert os.path.exists(GPU_BIN), "kpop_b200/bin/KPopCount is missing: __graft_entry__.build() makes it"
+    rc, out, err = run_cli(GPU_BIN, ["-v", "-l", "x"])
+    assert b"backend: cuda" in err
+    return GPU_BIN
+
+
+@pytest.mark.parametrize("chunk", [None, 4096])
+@pytest.mark.parametrize("kat", KATS, ids=[k[0] for k in KATS])
+def test_gpu_kat(gpu_bin, tmp_path, kat, chunk):
+    name, files, argv, expected, code = kat
+    rc, out, err = run_cli(gpu_bin, materialise(tmp_path, files, argv), env=env_chunk(chunk))
+    assert rc == code, err.decode(errors="replace")
+    assert out == expected
+
+
+def test_gpu_k9_bucket_order(gpu_bin, tmp_path):
+    name, files, argv, head, code = K9
+    rc, out, err = run_cli(gpu_bin, materialise(tmp_path, files, argv))
+    assert rc == code
+    assert out.split(b"\n")[: len(head)] == head
+
+
+@pytest.fixture(scope="module")
+def fixture_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("fixtures")
+    for name in ("wuhan", "refTB", "clusters-small"):
+        with gzip.open(os.path.join(GOLDEN, "inputs", name + ".fasta.gz"), "rb") as src, open(d / (name + ".fasta"), "wb") as dst:
+            dst.write(src.read())
+    return str(d)
+
+
+@pytest.mark.parametrize("chunk", [None, 1_000_003])
+def test_gpu_reference_fixtures(gpu_bin, oracle_bin, fixture_dir, chunk):
+    """C1 / C2 of BASELINE.json and the k > 12 / -M orders, against the committed digests AND the oracle run here."""
+    with open(os.path.join(GOLDEN, "fixture_digests.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        argv = [a.replace("{REF_TEST}", fixture_dir) for a in c["argv"]]
+        rc, out, err = run_cli(gpu_bin, argv, env=env_chunk(chunk))
+        assert rc == 0, err.decode(errors="replace")
+        assert (out.count(b"\n"), len(out), hashlib.md5(out).hexdigest()) == (c["lines"], c["bytes"], c["md5"]), c["argv"]
+        rc_o, out_o, _ = run_cli(oracle_bin, argv)
+        assert out == out_o
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_gpu_fuzz_vs_oracle(gpu_bin, oracle_bin, tmp_path, seed):
+    rng = random.Random(5000 + seed)
+    for idx in range(25):
+        argv, fmt = one_case(rng, tmp_path, idx)
+        chunk = rng.choice([None, 4096, 70_000])
+        rc_o, out_o, err_o = run_cli(oracle_bin, argv)
+        rc_g, out_g, err_g = run_cli(gpu_bin, argv, env=env_chunk(chunk))
+        if rc_g == 2 and b"code -9" in err_g:
+            continue
+        ctx = f"seed={seed} case={idx} chunk={chunk} argv={' '.join(argv)}\n{err_g.decode(errors='replace')}"
+        assert rc_g == rc_o, ctx
+        assert out_g == out_o, ctx
+
+
+def test_gpu_longer_inputs_every_mode(gpu_bin, oracle_bin, tmp_path):
+    """A few hundred kB per input so that many tiles, look-backs and launches are involved."""
+    rng = random.Random(99)
+    fa = tmp_path / "big.fa"
+    fa.write_bytes(b"".join(fasta(rng, max_records=6, max_len=40000) for _ in range(8)))
+    fq = tmp_path / "big.fq"
+    parts = []
+    for i in range(3000):
+        n = rng.randrange(20, 260)
+        seq = bytes(rng.choices(b"ACGTN", weights=[30, 30, 30, 30, 1], k=n))
+        parts.append(b"@r%d\n%s\n+\n%s\n" % (i, seq, b"I" * n))
+    fq.write_bytes(b"".join(parts))
+    cases = [["-k", "12", "-l", "x", "-f", str(fa)], ["-k", "5", "-L", "-f", str(fa)], ["-k", "17", "-l", "x", "-f", str(fa)],
+             ["-k", "30", "-L", "-f", str(fa)], ["-k", "9", "-M", "5000", "-l", "x", "-f", str(fa)],
+             ["-k", "12", "-l", "x", "-s", str(fq)], ["-k", "12", "-C", "DNA-ss", "-l", "x", "-s", str(fq)],
+             ["-k", "21", "-l", "x", "-s", str(fq)], ["-k", "7", "-L", "-s", str(fq)], ["-k", "13", "-M", "20000", "-l", "x", "-s", str(fq)],
+             ["-k", "12", "-l", "x", "-p", str(fq), str(fq)], ["-k", "6", "-C", "protein", "-l", "x", "-f", str(fa)]]
+    for argv in cases:
+        for chunk in (None, 50_000):
+            rc_o, out_o, _ = run_cli(oracle_bin, argv)
+            rc_g, out_g, err_g = run_cli(gpu_bin, argv, env=env_chunk(chunk))
+            assert (rc_g, out_g) == (rc_o, out_o), f"{argv} chunk={chunk}\n{err_g.decode(errors='replace')[-400:]}"
+
+
+# ---- synthetic reads of the benchmark shape, through the Python binding of the C ABI ------------------------------
+def _fastdense():
+    from test_oracle_fastdense import fastdense
+    return fastdense()
+
+
+def test_gpu_synth_generator_matches_host_generator():
+    import torch
+    from kpop_b200 import KMerCounter
+    host = subprocess.run([SYNTH, "12345", "5000", "3"], stdout=subprocess.PIPE, check=True).stdout
+    with KMerCounter(k=12, label="x") as kc:
+        n = kc.synth_offset(12345 + 5000) - kc.synth_offset(12345)
+        assert n == len(host)
+        dev = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+        kc.synth_fastq(dev.data_ptr(), 12345, 5000, 3)
+        assert bytes(dev[:n].cpu().numpy()) == host
+
+
+def _device_table(kc):
+    import torch
+    from kpop_b200.distributed import table_views
+    lo, _ = table_views(kc)
+    return lo.cpu().numpy().view(np.uint32)
+
+
+@pytest.mark.parametrize("n_rec", [1, 37, 20_000, 600_000])
+def test_gpu_synth_device_feed_vs_cpu_checker(n_rec):
+    """kpc_feed_device (the benchmark's entry point) against the CPU dense counter, bin by bin, and the text."""
+    import torch
+    from kpop_b200 import KMerCounter
+    host = subprocess.run([SYNTH, "0", str(n_rec), "3"], stdout=subprocess.PIPE, check=True).stdout
+    lib = _fastdense()
+    want = np.zeros(4 ** 12, dtype=np.uint32)
+    lib.fd_count_fastq_dense(host, len(host), 12, want.ctypes.data_as(ctypes.c_void_p), 8)
+    with KMerCounter(k=12, label="S") as kc:
+        dev = torch.empty(len(host) + 64, dtype=torch.uint8, device="cuda")
+        kc.synth_fastq(dev.data_ptr(), 0, n_rec, 3)
+        kc.begin("single-end")
+        kc.feed_device(dev.data_ptr(), len(host), eof=True)
+        kc.end()
+        got = _device_table(kc)
+        assert np.array_equal(got, want)
+        assert kc.kmers_counted() == int(want.sum()) == lib.fd_synth_valid_windows(0, n_rec, 3, 12, 4)
+        kc.finish()
+        text = kc.take_text()
+        nz = np.nonzero(want)[0]
+        assert text.count(b"\n") == len(nz) + 1
+        assert text.startswith(b"\tS\n%06x\t%d\n" % (nz[0], want[nz[0]]))
+        # host feed from pinned memory gives the same bytes
+        kc.reset()
+        pinned = torch.empty(len(host), dtype=torch.uint8, pin_memory=True)
+        pinned.copy_(torch.frombuffer(bytearray(host), dtype=torch.uint8))
+        kc.begin("single-end")
+        kc.feed_pointer(pinned.data_ptr(), len(host), eof=True)
+        kc.end()
+        kc.finish()
+        assert kc.take_text() == text
+
+
+def test_gpu_truncated_synthetic_stream_drops_the_last_record():
+    import torch
+    from kpop_b200 import KMerCounter
+    host = subprocess.run([SYNTH, "0", "4000", "3"], stdout=subprocess.PIPE, check=True).stdout
+    lib = _fastdense()
+    for cut in (1, 100, 152, 160, 312):
+        part = host[: len(host) - cut]
+        want = np.zeros(4 ** 12, dtype=np.uint32)
+        lib.fd_count_fastq_dense(part, len(part), 12, want.ctypes.data_as(ctypes.c_void_p), 4)
+        with KMerCounter(k=12, label="S") as kc:
+            dev = torch.zeros(len(part) + 64, dtype=torch.uint8, device="cuda")
+            dev[: len(part)] = torch.frombuffer(bytearray(part), dtype=torch.uint8).cuda()
+            kc.begin("single-end")
+            kc.feed_device(dev.data_ptr(), len(part), eof=True)
+            kc.end()
+            assert np.array_equal(_device_table(kc), want), cut
+
+
+def test_gpu_full_size_properties():
+    """BASELINE.json's single-GPU size (C3: 31,781,305 reads, 9,999,999,965 B): size-independent properties.
+    (1) the table sums to the number of valid windows of the stream (closed form from the generator);
+    (2) linearity: table(whole) == table(first part) + table(rest), cut at a record boundary;
+    (3) only canonical bins are ever touched;  (4) a 1 GB prefix agrees bin by bin with the CPU checker."""
+    import torch
+    from kpop_b200 import KMerCounter
+    R = 31_781_305
+    lib = _fastdense()
+    with KMerCounter(k=12, label="S3") as kc:
+        n = kc.synth_offset(R)
+        assert n == 9_999_999_965
+        dev = torch.empty(n + 256, dtype=torch.uint8, device="cuda")
+        kc.synth_fastq(dev.data_ptr(), 0, R, 3)
+
+        def table_of(offset, length):
+            kc.reset()
+            kc.begin("single-end")
+            kc.feed_device(dev.data_ptr() + offset, length, eof=True)
+            kc.end()
+            return _device_table(kc).astype(np.uint64)
+
+        whole = table_of(0, n)
+        assert int(whole.sum()) == lib.fd_synth_valid_windows(0, R, 3, 12, 16)
+        r_cut = 10_000_001
+        cut = kc.synth_offset(r_cut)
+        assert cut % 16 != 0 or True
+        # the second part must start 16-byte aligned for kpc_feed_device: pick a record whose offset is
+        while kc.synth_offset(r_cut) % 16:
+            r_cut += 1
+        cut = kc.synth_offset(r_cut)
+        a = table_of(0, cut)
+        b = table_of(cut, n - cut)
+        assert np.array_equal(a + b, whole)
+        # canonical bins only: key <= reverse complement
+        idx = np.nonzero(whole)[0].astype(np.uint64)
+        rc = np.zeros_like(idx)
+        x = idx.copy()
+        for _ in range(12):
+            rc = (rc << np.uint64(2)) | (np.uint64(3) - (x & np.uint64(3)))
+            x >>= np.uint64(2)
+        assert np.all(idx <= rc)
+        # 1 GB prefix against the CPU checker
+        r_pre = 3_178_130
+        pre = kc.synth_offset(r_pre)
+        host = dev[:pre].cpu().numpy().tobytes()
+        want = np.zeros(4 ** 12, dtype=np.uint32)
+        lib.fd_count_fastq_dense(host, len(host), 12, want.ctypes.data_as(ctypes.c_void_p), 16)
+        assert np.array_equal(table_of(0, pre), want.astype(np.uint64))
