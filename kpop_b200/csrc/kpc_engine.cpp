@@ -1,5 +1,6 @@
 // kpc_engine.cpp -- see kpc_engine.h.  Reference semantics cited inline (paths relative to the KPop tree).
 #include "kpc_engine.h"
+#include "kpc_fastq.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -90,6 +91,14 @@ KpcEngine::KpcEngine(const KpcEngineConfig &cfg) : cfg_(cfg) {
   chunk_cap_ = env_size("KPC_CHUNK_BYTES", (size_t)64 << 20);
   if (chunk_cap_ < 64) chunk_cap_ = 64;
   tile_bytes_ = kpc_k_tile_bytes();
+  {
+    const char *e = getenv("KPC_FAST");
+    fq_enabled_ = !(e && e[0] == '0');
+    fq_launch_bytes_ = env_size("KPC_FQ_LAUNCH_BYTES", (size_t)1 << 30);
+    const size_t tb = kpc_fq_tile_bytes();
+    fq_launch_bytes_ = std::max<size_t>(tb, fq_launch_bytes_ / tb * tb);
+    fq_launch_bytes_ = std::min<size_t>(fq_launch_bytes_, (size_t)2 << 30);  // u32 queue cursors, u32 tile indices
+  }
   tile_counter_ = (uint32_t *)rt_dmalloc(64);
   d_tmp_ = (unsigned long long *)rt_dmalloc(64 * sizeof(unsigned long long));
   h_tmp_ = (unsigned long long *)rt_hmalloc(64 * sizeof(unsigned long long));
@@ -143,6 +152,7 @@ KpcEngine::~KpcEngine() {
   rt_dfree(scratch_); rt_dfree(scratch2_);
   if (h_out_) rt_hfree(h_out_);
   rt_dfree(dense_lo_); rt_dfree(dense_hi_);
+  rt_dfree(fq_queue_); rt_dfree(fq_meta_); rt_dfree(fq_state_);
   rt_dfree(hkeys_); rt_dfree(hcounts_); rt_dfree(hranks_); rt_dfree(d_hstat_);
   rt_dfree(tkeys_); rt_dfree(tranks_); rt_dfree(trecs_); rt_dfree(d_tn_); rt_dfree(d_recs_);
   rt_stream_destroy(compute_);
@@ -233,7 +243,7 @@ uint64_t KpcEngine::grow_buckets(uint64_t size_reached) {
 // =================================================================================================
 void KpcEngine::reset_stream(StreamState &st) {
   st.fed = 0; st.hold_len = 0; st.cur = 0; st.eof = false; st.any = false; st.last_byte = '\n';
-  st.tail_unsafe = false; st.total_lines = 0; st.records = 0; st.final_recs = 0;
+  st.tail_unsafe = false; st.total_lines = 0; st.records = 0; st.final_recs = 0; st.at_line_start = true;
   KpcStreamCarry c;
   memset(&c, 0, sizeof c);
   c.s1 = kpc_s1_identity();
@@ -432,7 +442,9 @@ void KpcEngine::submit_host(StreamState &st, int mate, const Piece *pc, int npc,
     size_t o = 0;
     for (int i = 0; i < npc; ++i) { if (pc[i].n) memcpy(tag_bytes_.data() + o, pc[i].p, pc[i].n); o += pc[i].n; }
   }
-  run_launch(st, mate, slot.buf, len, final_launch);
+  run_launch(st, mate, slot.buf, len, final_launch, false);
+  for (int i = npc - 1; i >= 0; --i)
+    if (pc[i].n) { st.at_line_start = pc[i].p[pc[i].n - 1] == '\n'; break; }
   rt_event_record(slot.computed, compute_);
   slot.used = true;
 }
@@ -447,7 +459,7 @@ void KpcEngine::feed_device(int mate, const uint8_t *dev, size_t n, bool eof) {
   StreamState &st = streams_[mate];
   if (st.eof || st.fed || st.hold_len) throw KpcError(KPC_E_UNSUPPORTED, "kpc_feed_device cannot be mixed with kpc_feed");
   st.eof = true;
-  if (!n) { run_launch(st, mate, dev, 0, true); return; }
+  if (!n) { run_launch(st, mate, dev, 0, true, false); return; }
   st.any = true;
   // find the cut between the in-place body and the tail (last lines) on a host copy of the end of the input
   size_t win = std::min<size_t>(n, std::min<size_t>(chunk_cap_, (size_t)1 << 20));
@@ -467,7 +479,18 @@ void KpcEngine::feed_device(int mate, const uint8_t *dev, size_t n, bool eof) {
       if (cut >= 16) cut -= 16; else cut = 0;
     }
   }
-  if (cut) run_launch(st, mate, dev, cut, false);
+  if (cut) {
+    if (fq_usable()) {
+      // the fast pipeline works on bounded launches (its queues are sized for one): consecutive pieces of the same
+      // device buffer, so every piece but the first can read the 16 bytes before it
+      const size_t sub = fq_launch_bytes_;
+      for (size_t off = 0; off < cut; off += sub) run_launch(st, mate, dev + off, std::min(sub, cut - off), false, off > 0);
+    } else {
+      run_launch(st, mate, dev, cut, false, false);
+    }
+    const size_t w0 = n - win;
+    st.at_line_start = cut > w0 ? tail[cut - w0 - 1] == '\n' : false;
+  }
   RingSlot &slot = next_slot();
   if (slot.used) rt_stream_wait(compute_, slot.computed);
   size_t tl = n - cut;
@@ -477,7 +500,7 @@ void KpcEngine::feed_device(int mate, const uint8_t *dev, size_t n, bool eof) {
     rt_h2d(slot.buf + tl, h_tmp_ + 24, 1, compute_);
     tl += 1;
   }
-  run_launch(st, mate, slot.buf, tl, true);
+  run_launch(st, mate, slot.buf, tl, true, false);
   rt_event_record(slot.computed, compute_);
   slot.used = true;
 }
@@ -512,7 +535,79 @@ uint64_t KpcEngine::final_line_cap(StreamState &st, const uint8_t *dev, size_t l
   return recs * 4;
 }
 
-void KpcEngine::run_launch(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch) {
+// FASTQ + DNA + dense table + 8 <= k <= 12: the partition / shared-memory-count pipeline of kpc_fastq.cu
+bool KpcEngine::fq_usable() const {
+  return fq_enabled_ && mode_ == DENSE && format_ != KPC_FASTA && kpc_fq_supported(cfg_.k, cfg_.content);
+}
+
+void KpcEngine::fq_ensure(size_t len) {
+  if (len <= fq_alloc_len_) return;
+  rt_stream_sync(compute_);
+  rt_dfree(fq_queue_); rt_dfree(fq_meta_); rt_dfree(fq_state_);
+  fq_queue_ = nullptr; fq_meta_ = nullptr; fq_state_ = nullptr;
+  fq_alloc_len_ = std::max<size_t>(len, std::min<size_t>(fq_launch_bytes_, (size_t)8 << 20));
+  fq_log_bins_ = kpc_fq_log_bins(cfg_.k);
+  fq_slices_ = (uint32_t)(nbins_ >> fq_log_bins_);
+  // every byte yields at most one k-mer.  DNA-ds keys are min(f, rc): their density falls off linearly with the
+  // slice index (2 (1 - b/S) / S for uniform reads); DNA-ss keys are uniform.  Capacities leave >= 1.5x head-room
+  // over that at one k-mer per byte (FASTQ has ~0.45); anything beyond is counted in place by the kernel.
+  std::vector<unsigned long long> base(fq_slices_);
+  std::vector<uint32_t> cap(fq_slices_);
+  unsigned long long total = 0;
+  for (uint32_t b = 0; b < fq_slices_; ++b) {
+    double wgt = cfg_.content == KPC_DNA_DS ? 0.5 + 2.5 * (1.0 - (double)b / fq_slices_) : 2.0;
+    unsigned long long c = (unsigned long long)((double)fq_alloc_len_ * wgt / fq_slices_) + 64;
+    c = (c + 7) & ~7ull;
+    if (c > 0xfffffff0ull) c = 0xfffffff0ull;
+    base[b] = total;
+    cap[b] = (uint32_t)c;
+    total += c;
+  }
+  fq_queue_ = (uint16_t *)rt_dmalloc(total * sizeof(uint16_t) + 64);
+  // meta: [0, 64) claim counters | cursors | capacities | bases
+  const size_t cur_off = 64, cap_off = cur_off + 4 * (size_t)fq_slices_, base_off = (cap_off + 4 * (size_t)fq_slices_ + 7) & ~(size_t)7;
+  fq_meta_ = (uint8_t *)rt_dmalloc(base_off + 8 * (size_t)fq_slices_);
+  fq_zero_bytes_ = cap_off;
+  fq_cur_off_ = cur_off; fq_cap_off_ = cap_off; fq_base_off_ = base_off;
+  rt_h2d(fq_meta_ + cap_off, cap.data(), 4 * (size_t)fq_slices_, compute_);
+  rt_h2d(fq_meta_ + base_off, base.data(), 8 * (size_t)fq_slices_, compute_);
+  rt_stream_sync(compute_);  // the vectors go out of scope
+  fq_state_tiles_ = (fq_alloc_len_ + kpc_fq_tile_bytes() - 1) / kpc_fq_tile_bytes() + 1;
+  fq_state_ = (unsigned long long *)rt_dmalloc(fq_state_tiles_ * 8);
+}
+
+void KpcEngine::fq_launch(StreamState &st, const uint8_t *dev, size_t len, uint64_t max_lines, bool halo_ok) {
+  fq_ensure(len);
+  KpcFqLaunch L;
+  memset(&L, 0, sizeof L);
+  L.data = dev;
+  L.n = len;
+  L.abs_base = st.fed;
+  L.halo_ok = halo_ok ? 1 : 0;
+  L.max_lines = max_lines;
+  L.k = cfg_.k;
+  L.content = cfg_.content;
+  L.carry_in = st.carry[st.cur];
+  L.carry_out = st.carry[st.cur ^ 1];
+  L.err_line = st.err_line;
+  L.tile_state = fq_state_;
+  L.counters = (uint32_t *)fq_meta_;
+  L.n_tiles = (uint32_t)((len + kpc_fq_tile_bytes() - 1) / kpc_fq_tile_bytes());
+  L.log_bins = fq_log_bins_;
+  L.n_slices = fq_slices_;
+  L.queue = fq_queue_;
+  L.qbase = (const unsigned long long *)(fq_meta_ + fq_base_off_);
+  L.qcap = (const uint32_t *)(fq_meta_ + fq_cap_off_);
+  L.qcursor = (uint32_t *)(fq_meta_ + fq_cur_off_);
+  L.table = dense_lo_;
+  rt_memset(fq_state_, 0, (size_t)L.n_tiles * 8, compute_);
+  rt_memset(fq_meta_, 0, fq_zero_bytes_, compute_);
+  kpc_fq_partition(L, compute_);
+  kpc_fq_count(L, compute_);
+  launches_ += 2;
+}
+
+void KpcEngine::run_launch(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch, bool halo_ok) {
   uint64_t max_lines = ~0ull;
   if (format_ != KPC_FASTA) {
     if (final_launch) max_lines = final_line_cap(st, dev, len);
@@ -520,9 +615,10 @@ void KpcEngine::run_launch(StreamState &st, int mate, const uint8_t *dev, size_t
   }
   switch (mode_) {
     case DENSE: {
-      KpcDenseSink ds{dense_lo_};
-      (void)ds;
-      launch_tiles(st, mate, dev, len, final_launch, max_lines, KPC_SINK_DENSE, nullptr, nullptr, false, nullptr, 0);
+      if (len && fq_usable() && (halo_ok || st.at_line_start) && len <= fq_launch_bytes_)
+        fq_launch(st, dev, len, max_lines, halo_ok);
+      else
+        launch_tiles(st, mate, dev, len, final_launch, max_lines, KPC_SINK_DENSE, nullptr, nullptr, false, nullptr, 0);
       advance(st, len);
       dense_after_launch(len);
       break;

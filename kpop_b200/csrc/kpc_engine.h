@@ -77,6 +77,7 @@ class KpcEngine {
     bool any = false;
     uint8_t last_byte = '\n';
     bool tail_unsafe = false;
+    bool at_line_start = true;  // the next launch begins at the first byte of a line
     uint64_t total_lines = 0;
     uint64_t records = 0;     // FASTQ: complete records (known at end of file); FASTA: header lines
     uint64_t final_recs = 0;  // -L: records of this mate that can be written out
@@ -92,7 +93,10 @@ class KpcEngine {
   void hold_append(StreamState &st, const uint8_t *p, size_t n);
   size_t choose_cut(StreamState &st, const Piece *pc, int npc, size_t limit);
   void submit_host(StreamState &st, int mate, const Piece *pc, int npc, size_t len, bool final_launch, bool foreign);
-  void run_launch(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch);
+  void run_launch(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch, bool halo_ok);
+  bool fq_usable() const;
+  void fq_ensure(size_t len);
+  void fq_launch(StreamState &st, const uint8_t *dev, size_t len, uint64_t max_lines, bool halo_ok);
   uint64_t final_line_cap(StreamState &st, const uint8_t *dev, size_t len);
   RingSlot &next_slot();
 
@@ -168,6 +172,16 @@ class KpcEngine {
   uint32_t *dense_lo_ = nullptr;
   unsigned long long *dense_hi_ = nullptr;
   uint64_t dense_since_fold_ = 0;
+
+  // fast FASTQ pipeline (kpc_fastq.h)
+  bool fq_enabled_ = true;
+  size_t fq_launch_bytes_ = 0, fq_alloc_len_ = 0, fq_state_tiles_ = 0;
+  size_t fq_zero_bytes_ = 0, fq_cur_off_ = 0, fq_cap_off_ = 0, fq_base_off_ = 0;
+  int fq_log_bins_ = 15;
+  uint32_t fq_slices_ = 0;
+  uint16_t *fq_queue_ = nullptr;
+  uint8_t *fq_meta_ = nullptr;
+  unsigned long long *fq_state_ = nullptr;
 
   // hash
   unsigned long long *hkeys_ = nullptr, *hcounts_ = nullptr, *hranks_ = nullptr;

@@ -1,0 +1,50 @@
+// kpc_fastq.h -- launch interface of the fast FASTQ / dense-table pipeline (kpc_fastq.cu).
+//
+// The generic tile machine (kpc_tile.cuh) sends one RED per k-mer to the L2-resident 4^k table; on a B200 that
+// caps the k = 12 path at ~190 G k-mers/s (profiles/r1_microbench_primitives.jsonl).  This pipeline replaces it
+// for FASTQ + DNA + dense table, 8 <= k <= 12, with two kernels per launch of the byte stream:
+//
+//   fq_partition   record framing (Files.FASTQ.iter_se, Files.ml:201-221) + linting (Sequences.ml:41-67) +
+//                  forward / reverse-complement k-mers and min (KMers.ml:357-389), 16 windows per thread with
+//                  SIMD-in-register classification; the canonical keys of a tile are counting-sorted in shared
+//                  memory by their top bits ("slice") and appended, 16 bits per k-mer, to per-slice queues in HBM
+//   fq_count       one CTA per slice: the slice of the table (2^15 u32 bins) lives in shared memory, queue entries
+//                  are counted with shared-memory atomics, non-zero bins are added to the global table
+//                  (IntHashFrequencies.add, KMers.ml:107-111)
+//
+// Queues have a fixed capacity per slice; k-mers that do not fit (heavily skewed inputs) are counted directly in
+// the global table with RED, so the result is exact whatever the input.
+#pragma once
+#include "kpc_rt.h"
+#include "kpc_tile.cuh"
+
+struct KpcFqLaunch {
+  const uint8_t *data;      // launch bytes; 16-byte aligned; readable up to the next 16-byte boundary past n
+  uint64_t n;
+  uint64_t abs_base;        // stream offset of data[0]
+  int halo_ok;              // data[-16 .. 0) is readable and holds the 16 stream bytes before the launch
+                            // (otherwise the launch must start at a line start)
+  uint64_t max_lines;       // bytes on lines >= max_lines are ignored (incomplete last record, -p cap)
+  int k;
+  int content;              // KPC_CONTENT_DNA_SS / KPC_CONTENT_DNA_DS
+  const KpcStreamCarry *carry_in;
+  KpcStreamCarry *carry_out;
+  unsigned long long *err_line;
+  unsigned long long *tile_state;  // n_tiles words, zero on entry (newline-count look-back)
+  uint32_t *counters;              // [0] tile claim counter, [1] slice claim counter: zero on entry
+  uint32_t n_tiles;
+  // slices and queues
+  int log_bins;                    // bins per slice = 1 << log_bins (<= 15)
+  uint32_t n_slices;               // 4^k >> log_bins  (2 .. 512)
+  uint16_t *queue;
+  const unsigned long long *qbase; // first entry of every slice's queue (multiple of 8)
+  const uint32_t *qcap;            // capacity of every slice's queue, in entries
+  uint32_t *qcursor;               // entries appended so far (may exceed the capacity): zero on entry
+  uint32_t *table;                 // the dense 4^k table
+};
+
+uint32_t kpc_fq_tile_bytes();
+bool kpc_fq_supported(int k, int content);
+int kpc_fq_log_bins(int k);
+void kpc_fq_partition(const KpcFqLaunch &L, rt_stream s);
+void kpc_fq_count(const KpcFqLaunch &L, rt_stream s);

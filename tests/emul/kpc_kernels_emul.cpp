@@ -11,6 +11,7 @@
 
 #include "../../include/kpopcount.h"
 #include "../../kpop_b200/csrc/kpc_kernels.h"
+#include "../../kpop_b200/csrc/kpc_fastq.h"
 #include "../../kpop_b200/csrc/kpc_synth.h"
 
 namespace {
@@ -79,6 +80,14 @@ void kpc_k_tiles(const KpcTileLaunch &L, rt_stream) {
   else if (g_nt == 256 && g_seg == 64) run_f<256, 64>(L);
   else throw KpcError(KPC_E_ARG, "KPC_EMUL_TILE: unsupported geometry");
 }
+
+// the fast FASTQ pipeline (kpc_fastq.cu) is warp-level CUDA and has no host rendition: the emulated engine
+// always takes the generic tile machine
+uint32_t kpc_fq_tile_bytes() { return 32768; }
+bool kpc_fq_supported(int, int) { return false; }
+int kpc_fq_log_bins(int) { return 15; }
+void kpc_fq_partition(const KpcFqLaunch &, rt_stream) { throw KpcError(KPC_E_STATE, "emulation: no fast FASTQ path"); }
+void kpc_fq_count(const KpcFqLaunch &, rt_stream) { throw KpcError(KPC_E_STATE, "emulation: no fast FASTQ path"); }
 
 void kpc_k_count_newlines(const uint8_t *d, uint64_t n, unsigned long long *out, rt_stream) {
   unsigned long long c = 0;
