@@ -548,16 +548,15 @@ void KpcEngine::fq_ensure(size_t len) {
   fq_alloc_len_ = std::max<size_t>(len, std::min<size_t>(fq_launch_bytes_, (size_t)8 << 20));
   fq_log_bins_ = kpc_fq_log_bins(cfg_.k);
   fq_slices_ = (uint32_t)(nbins_ >> fq_log_bins_);
-  // every byte yields at most one k-mer.  DNA-ds keys are min(f, rc): their density falls off linearly with the
-  // slice index (2 (1 - b/S) / S for uniform reads); DNA-ss keys are uniform.  Capacities leave >= 1.5x head-room
-  // over that at one k-mer per byte (FASTQ has ~0.45); anything beyond is counted in place by the kernel.
+  // every byte yields at most one k-mer (FASTQ of 150-base reads has ~0.45) and slices are cut out of the middle
+  // of the key, where canonical k-mers of uniform reads are uniform: capacities are 1.25 k-mers per byte spread
+  // evenly, plus the padding the CTAs leave behind; anything beyond is counted in place by the kernel.
   std::vector<unsigned long long> base(fq_slices_);
   std::vector<uint32_t> cap(fq_slices_);
   unsigned long long total = 0;
   for (uint32_t b = 0; b < fq_slices_; ++b) {
-    double wgt = cfg_.content == KPC_DNA_DS ? 0.5 + 2.5 * (1.0 - (double)b / fq_slices_) : 2.0;
-    unsigned long long c = (unsigned long long)((double)fq_alloc_len_ * wgt / fq_slices_) + 64;
-    c = (c + 7) & ~7ull;
+    unsigned long long c = (unsigned long long)((double)fq_alloc_len_ * 1.25 / fq_slices_) + kpc_fq_queue_slack();
+    c = (c + 15) & ~15ull;
     if (c > 0xfffffff0ull) c = 0xfffffff0ull;
     base[b] = total;
     cap[b] = (uint32_t)c;
@@ -594,6 +593,8 @@ void KpcEngine::fq_launch(StreamState &st, const uint8_t *dev, size_t len, uint6
   L.counters = (uint32_t *)fq_meta_;
   L.n_tiles = (uint32_t)((len + kpc_fq_tile_bytes() - 1) / kpc_fq_tile_bytes());
   L.log_bins = fq_log_bins_;
+  L.lo_bits = kpc_fq_lo_bits(cfg_.k);
+  L.slice_bits = 2 * cfg_.k - fq_log_bins_;
   L.n_slices = fq_slices_;
   L.queue = fq_queue_;
   L.qbase = (const unsigned long long *)(fq_meta_ + fq_base_off_);

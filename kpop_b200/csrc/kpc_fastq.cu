@@ -13,8 +13,11 @@
 //      FQ_W window-end positions; a scan over the rows gives every unit a number
 //   4. one thread per unit: 12 + 16 bytes -> 2-bit codes + validity bits with SIMD-in-register arithmetic,
 //      forward and reverse-complement words, 16 canonical keys in registers
-//   5. counting sort of the keys by slice in shared memory (histogram, scan, scatter), then every slice's run is
-//      appended to its queue in HBM with a single reservation per (round, slice)
+//   5. software write-combining: every key is appended (one shared-memory atomic) to the bucket of its slice in
+//      shared memory; full 32-byte chunks of a bucket are reserved in the slice's queue in HBM (one global atomic per
+//      slice and round, issued early so that its latency hides behind the next round's k-mer arithmetic) and copied
+//      out with 128-bit stores.  The slice is taken from the MIDDLE bits of the key: min(f, rc) skews the top and
+//      the bottom bases of a canonical k-mer but leaves the central ones uniform, so the buckets fill evenly.
 #include <cuda_runtime.h>
 
 #include <string>
@@ -43,21 +46,23 @@ constexpr int FQ_MAXROWS = FQ_NT;                 // sequence lines per batch
 constexpr int FQ_MAXSLOTS = 4 * FQ_NT;            // lines per batch
 constexpr int FQ_MAXSLICES = 512;
 constexpr int FQ_BIAS = 17;                       // positions are stored + FQ_BIAS (they start at -17)
-constexpr int FQ_LPG = 16;                        // lanes per slice in the copy-out
+constexpr int FQ_BUCKET_ENTRIES = 24576;          // shared-memory bucket space (u16 entries) shared by all slices
+constexpr int FQ_CHUNK = 16;                      // entries per copy-out chunk (32 bytes: one L2 sector)
+constexpr int FQ_RETRIES = 2;                     // rounds of bucket overflow before keys are counted in place
+constexpr uint16_t FQ_PAD = 0xFFFFu;              // queue entry that pads the last chunk of a CTA (skipped by fq_count)
 static_assert(FQ_PIECES * FQ_NW % 32 == 0, "census scan layout");
 static_assert(FQ_MAXSLICES <= FQ_NT, "one thread per slice in the scan");
 
 struct FqSmem {
   alignas(16) uint8_t raw[FQ_HALO + FQ_TB + 48];  // raw[16 + i] = tile byte i
-  alignas(16) uint16_t sorted[FQ_NT * FQ_W];
-  unsigned long long qbase[FQ_MAXSLICES];
+  alignas(16) uint16_t bucket[FQ_BUCKET_ENTRIES + 2 * FQ_CHUNK];  // slice s owns [s * cap, (s + 1) * cap)
   unsigned long long G;                           // number of '\n' in the stream before the tile
-  uint32_t qcap[FQ_MAXSLICES];
-  uint32_t hist[FQ_MAXSLICES], cnt[FQ_MAXSLICES], offs[FQ_MAXSLICES], cur[FQ_MAXSLICES], gpos[FQ_MAXSLICES];
+  uint32_t fill[FQ_MAXSLICES];                    // entries in the bucket (may run past cap while appending)
+  uint32_t fl_g[FQ_MAXSLICES];                    // queue position reserved for the chunks being copied out
+  uint32_t fl_n[FQ_MAXSLICES];                    // entries being copied out (multiple of FQ_CHUNK)
   uint32_t ubase[FQ_MAXROWS + 1];
   uint32_t wtot_a[FQ_PIECES * FQ_NW];
   uint32_t wtot_b[32];
-  uint32_t wtot_c[32];
   uint32_t tileq[2];
   int head;                                       // position of the last '\n' before the tile (-1 .. -16), or -17
   uint16_t nlpos[FQ_MAXSLOTS + 2];
@@ -117,6 +122,16 @@ __device__ __forceinline__ void classify4(uint32_t w, uint32_t &codes8, uint32_t
   valid4 = (((nz >> 7) * 0x08040201u) >> 24) ^ 0xFu;
 }
 
+
+// slice / bin of a key and back: slice = key bits [lo, lo + sb), bin = the other bits packed together
+__device__ __forceinline__ uint32_t fq_slice_of(uint32_t key, int lo, uint32_t smask) { return (key >> lo) & smask; }
+__device__ __forceinline__ uint32_t fq_bin_of(uint32_t key, int lo, int sb, uint32_t lomask) {
+  return ((key >> (lo + sb)) << lo) | (key & lomask);
+}
+__device__ __forceinline__ uint32_t fq_key_of(uint32_t slice, uint32_t bin, int lo, int sb, uint32_t lomask) {
+  return ((bin >> lo) << (lo + sb)) | (slice << lo) | (bin & lomask);
+}
+
 // number of '\n' before the tile: decoupled look-back over one word per tile (2 status bits + 62 value bits)
 constexpr unsigned long long FQ_ST_AGG = 1ull << 62, FQ_ST_INC = 2ull << 62, FQ_VAL = (1ull << 62) - 1ull;
 __device__ __forceinline__ unsigned long long lookback(unsigned long long *state, uint32_t tile, uint32_t total,
@@ -150,6 +165,62 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long *state
   return acc;
 }
 
+
+// ---- bucket copy-out (step 5) ------------------------------------------------------------------------------------
+// reserve: thread s owns slice s.  Called after a barrier that follows the appends.  Whole chunks of the bucket are
+// reserved in the slice's queue; the result of the atomic is not needed before fq_flush_copy.
+__device__ __forceinline__ void fq_flush_reserve(FqSmem &S, const KpcFqLaunch &p, int tid, uint32_t NS, uint32_t cap,
+                                                 bool final, uint32_t &my_n, uint32_t &my_g) {
+  my_n = 0; my_g = 0;
+  if ((uint32_t)tid < NS) {
+    uint32_t f = S.fill[tid];
+    if (f > cap) f = cap;
+    uint32_t n = f & ~(uint32_t)(FQ_CHUNK - 1);
+    if (final && n < f) {  // the CTA is leaving: pad the last chunk
+      for (uint32_t i = f; i < n + FQ_CHUNK; ++i) S.bucket[tid * cap + i] = FQ_PAD;
+      n += FQ_CHUNK;
+      f = n;
+    }
+    S.fill[tid] = f - n;
+    my_n = n;
+    if (n) my_g = atomicAdd(p.qcursor + tid, n);
+  }
+}
+// copy: two lanes per slice move the reserved chunks with 128-bit accesses, then the bucket's remainder (< one
+// chunk) moves to the front.  Ends with a barrier: the buckets may be appended to again.
+__device__ __forceinline__ void fq_flush_copy(FqSmem &S, const KpcFqLaunch &p, int tid, uint32_t NS, uint32_t cap,
+                                              uint32_t my_n, uint32_t my_g, int lo, int sb, uint32_t lomask) {
+  if ((uint32_t)tid < NS) { S.fl_n[tid] = my_n; S.fl_g[tid] = my_g; }
+  __syncthreads();
+  const int half = 8 * (tid & 1);
+  for (uint32_t s = tid >> 1; s < NS; s += FQ_NT / 2) {
+    const uint32_t n = S.fl_n[s];
+    if (!n) continue;
+    const uint32_t g = S.fl_g[s];
+    const uint32_t qc = __ldg(p.qcap + s);
+    uint16_t *dst = p.queue + __ldg(p.qbase + s) + g + half;
+    uint16_t *src = S.bucket + s * cap + half;
+    for (uint32_t c = 0; c < n; c += FQ_CHUNK) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(src + c);
+      if (g + c + FQ_CHUNK <= qc) {
+        *reinterpret_cast<uint4 *>(dst + c) = v;
+      } else {  // queue full: count in place
+        const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t e = (ww[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+          if (e != FQ_PAD) atomicAdd(p.table + fq_key_of(s, e, lo, sb, lomask), 1u);
+        }
+      }
+    }
+    if (n < cap) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(src + n);
+      *reinterpret_cast<uint4 *>(src) = v;
+    }
+  }
+  __syncthreads();
+}
+
 template <bool DS, int KT>
 __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunch p) {
   extern __shared__ __align__(16) uint8_t fq_smem_raw[];
@@ -157,15 +228,16 @@ __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunc
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int k = KT ? KT : p.k;
   const uint32_t kmask = (k >= 16) ? 0xffffffffu : ((1u << (2 * k)) - 1u);
-  const int lb = p.log_bins;
-  const uint32_t binmask = (1u << lb) - 1u;
-  const uint32_t NS = p.n_slices;
+  const int slo = KT == 12 ? 7 : p.lo_bits;           // slice = key bits [slo, slo + sb)
+  const int sb = KT == 12 ? 9 : p.slice_bits;
+  const uint32_t NS = KT == 12 ? 512u : p.n_slices;
+  const uint32_t smask = NS - 1u, lomask = (1u << slo) - 1u;
+  const uint32_t cap = (uint32_t)FQ_BUCKET_ENTRIES / NS;  // bucket capacity per slice: a multiple of FQ_CHUNK
+  uint32_t my_n = 0, my_g = 0;                           // copy-out in flight for slice tid
+  bool flush_pending = false;
+  uint32_t next_tile = 0;                                // thread 0: the tile claimed for the next iteration
 
-  if (tid < FQ_MAXSLICES) {
-    S.hist[tid] = 0;
-    S.qcap[tid] = tid < NS ? p.qcap[tid] : 0u;
-    S.qbase[tid] = tid < NS ? p.qbase[tid] : 0ull;
-  }
+  if (tid < FQ_MAXSLICES) S.fill[tid] = 0;
   if (tid < 48) S.raw[FQ_HALO + FQ_TB + tid] = 0;
   if (tid == 0) S.tileq[0] = atomicAdd(p.counters, 1u);
   __syncthreads();
@@ -209,7 +281,7 @@ __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunc
       for (int q = 0; q < FQ_PIECES; ++q) S.wtot_a[q * FQ_NW + w] = inc[q];
     }
     __syncthreads();  // (1) raw[] and wtot_a[] are complete
-    if (tid == 0) S.tileq[(it + 1) & 1] = atomicAdd(p.counters, 1u);
+    bool claimed = false;
 
     // newline index of the first newline of every piece (pieces are ordered (q, thread))
     uint32_t base[FQ_PIECES];
@@ -404,56 +476,65 @@ __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunc
             key[jw] = f;
           }
         }
-        // histogram by slice
-#pragma unroll
-        for (int jw = 0; jw < FQ_W; ++jw)
-          if ((ok >> (FQ_W - 1 - jw)) & 1u) atomicAdd(&S.hist[key[jw] >> lb], 1u);
-        __syncthreads();  // (a)
-        {
-          uint32_t cn = 0;
-          if (tid < FQ_MAXSLICES) { cn = S.hist[tid]; S.hist[tid] = 0; }
-          uint32_t tot;
-          const uint32_t ex = block_excl_scan(cn, S.wtot_c, tot, lane, w);  // (b)
-          if (tid < FQ_MAXSLICES) {
-            S.cnt[tid] = cn; S.offs[tid] = ex; S.cur[tid] = ex;
-            S.gpos[tid] = cn ? atomicAdd(p.qcursor + tid, cn) : 0u;
-          }
+        // ---- 5. append to the buckets; whole chunks go out to the queues ----------------------------------------
+        // the next tile is claimed as late as possible (tiles are published in claim order: an early claim makes every
+        // later tile wait for this CTA), but early enough for the atomic to return before the tile ends
+        if (!claimed && hi == N + 1u && q0 + FQ_NT >= U) {
+          if (tid == 0) next_tile = atomicAdd(p.counters, 1u);
+          claimed = true;
         }
-        __syncthreads();  // (c)
+        uint32_t pending = ok;
+        for (int tries = 0;; ++tries) {
+          if (flush_pending) {  // the copy-out reserved after the previous round (its atomic has had time to return)
+            fq_flush_copy(S, p, tid, NS, cap, my_n, my_g, slo, sb, lomask);
+            flush_pending = false;
+          }
 #pragma unroll
-        for (int jw = 0; jw < FQ_W; ++jw)
-          if ((ok >> (FQ_W - 1 - jw)) & 1u) {
-            const uint32_t pos = atomicAdd(&S.cur[key[jw] >> lb], 1u);
-            S.sorted[pos] = (uint16_t)(key[jw] & binmask);
+          for (int jw = 0; jw < FQ_W; ++jw) {
+            const uint32_t bit = 1u << (FQ_W - 1 - jw);
+            if (pending & bit) {
+              const uint32_t sl = fq_slice_of(key[jw], slo, smask);
+              const uint32_t pos = atomicAdd(&S.fill[sl], 1u);
+              if (pos < cap) {
+                S.bucket[sl * cap + pos] = (uint16_t)fq_bin_of(key[jw], slo, sb, lomask);
+                pending &= ~bit;
+              } else if (tries >= FQ_RETRIES) {  // a slice that keeps overflowing (skewed input): count in place
+                atomicAdd(p.table + key[jw], 1u);
+                pending &= ~bit;
+              }
+            }
           }
-        __syncthreads();  // (d)
-        // copy-out: FQ_LPG lanes per slice
-        for (uint32_t b = tid / FQ_LPG; b < NS; b += FQ_NT / FQ_LPG) {
-          const uint32_t cn = S.cnt[b];
-          if (!cn) continue;
-          const uint32_t o = S.offs[b], g = S.gpos[b], cap = S.qcap[b];
-          uint16_t *dst = p.queue + S.qbase[b];
-          for (uint32_t l = tid % FQ_LPG; l < cn; l += FQ_LPG) {
-            const uint16_t ent = S.sorted[o + l];
-            const uint32_t pz = g + l;
-            if (pz < cap) dst[pz] = ent;
-            else atomicAdd(p.table + (((size_t)b << lb) | ent), 1u);  // queue full: count in place
-          }
+          const int any = __syncthreads_or(pending != 0u);
+          fq_flush_reserve(S, p, tid, NS, cap, false, my_n, my_g);
+          flush_pending = true;
+          if (!any) break;
         }
       }
     }
+    if (!claimed && tid == 0) next_tile = atomicAdd(p.counters, 1u);
+    if (tid == 0) S.tileq[(it + 1) & 1] = next_tile;
     __syncthreads();  // the next tile overwrites raw[], nlpos[] and the scan scratch
   }
+  // the CTA leaves: everything still in the buckets goes out, the last chunk of every slice padded
+  if (flush_pending) fq_flush_copy(S, p, tid, NS, cap, my_n, my_g, slo, sb, lomask);
+  fq_flush_reserve(S, p, tid, NS, cap, true, my_n, my_g);
+  fq_flush_copy(S, p, tid, NS, cap, my_n, my_g, slo, sb, lomask);
 }
 
 // one CTA per slice at a time: shared-memory histogram of the slice's queue, then RED of the non-zero bins
 constexpr int FQ_CNT_NT = 1024;
+__device__ __forceinline__ void fq_count2(uint32_t *tbl, uint32_t x) {
+  const uint32_t a = x & 0xFFFFu, b = x >> 16;
+  if (a != FQ_PAD) atomicAdd(&tbl[a], 1u);
+  if (b != FQ_PAD) atomicAdd(&tbl[b], 1u);
+}
 __global__ void __launch_bounds__(FQ_CNT_NT, 1) fq_count_kernel(const KpcFqLaunch p) {
   extern __shared__ __align__(16) uint8_t fq_smem_raw[];
   uint32_t *tbl = reinterpret_cast<uint32_t *>(fq_smem_raw);
   __shared__ uint32_t s_slice;
   const int tid = threadIdx.x;
-  const int lb = p.log_bins;
+  const int lb = p.log_bins, slo = p.lo_bits, sb = p.slice_bits;
+  const uint32_t lomask = (1u << slo) - 1u;
   const uint32_t nbins = 1u << lb;
   for (uint32_t i = tid; i < nbins; i += FQ_CNT_NT) tbl[i] = 0;
   for (;;) {
@@ -464,37 +545,26 @@ __global__ void __launch_bounds__(FQ_CNT_NT, 1) fq_count_kernel(const KpcFqLaunc
     if (b >= p.n_slices) break;
     uint32_t cn = p.qcursor[b];
     const uint32_t cap = p.qcap[b];
-    if (cn > cap) cn = cap;
+    if (cn > cap) cn = cap;  // both are multiples of FQ_CHUNK
     if (!cn) continue;
-    const uint16_t *src = p.queue + p.qbase[b];
+    const uint4 *sv = reinterpret_cast<const uint4 *>(p.queue + p.qbase[b]);
     const uint32_t nvec = cn >> 3;
-    const uint4 *sv = reinterpret_cast<const uint4 *>(src);
     uint32_t v = tid;
     for (; v + 3u * FQ_CNT_NT < nvec; v += 4u * FQ_CNT_NT) {
       uint4 x[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) x[u] = ldg_stream(reinterpret_cast<const uint8_t *>(sv + v + u * FQ_CNT_NT));
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        atomicAdd(&tbl[x[u].x & 0xFFFFu], 1u); atomicAdd(&tbl[x[u].x >> 16], 1u);
-        atomicAdd(&tbl[x[u].y & 0xFFFFu], 1u); atomicAdd(&tbl[x[u].y >> 16], 1u);
-        atomicAdd(&tbl[x[u].z & 0xFFFFu], 1u); atomicAdd(&tbl[x[u].z >> 16], 1u);
-        atomicAdd(&tbl[x[u].w & 0xFFFFu], 1u); atomicAdd(&tbl[x[u].w >> 16], 1u);
-      }
+      for (int u = 0; u < 4; ++u) { fq_count2(tbl, x[u].x); fq_count2(tbl, x[u].y); fq_count2(tbl, x[u].z); fq_count2(tbl, x[u].w); }
     }
     for (; v < nvec; v += FQ_CNT_NT) {
       const uint4 x = ldg_stream(reinterpret_cast<const uint8_t *>(sv + v));
-      atomicAdd(&tbl[x.x & 0xFFFFu], 1u); atomicAdd(&tbl[x.x >> 16], 1u);
-      atomicAdd(&tbl[x.y & 0xFFFFu], 1u); atomicAdd(&tbl[x.y >> 16], 1u);
-      atomicAdd(&tbl[x.z & 0xFFFFu], 1u); atomicAdd(&tbl[x.z >> 16], 1u);
-      atomicAdd(&tbl[x.w & 0xFFFFu], 1u); atomicAdd(&tbl[x.w >> 16], 1u);
+      fq_count2(tbl, x.x); fq_count2(tbl, x.y); fq_count2(tbl, x.z); fq_count2(tbl, x.w);
     }
-    for (uint32_t i = (nvec << 3) + tid; i < cn; i += FQ_CNT_NT) atomicAdd(&tbl[src[i]], 1u);
     __syncthreads();
-    uint32_t *out = p.table + ((size_t)b << lb);
     for (uint32_t i = tid; i < nbins; i += FQ_CNT_NT) {
       const uint32_t cv = tbl[i];
-      if (cv) { atomicAdd(out + i, cv); tbl[i] = 0; }
+      if (cv) { atomicAdd(p.table + fq_key_of(b, i, slo, sb, lomask), cv); tbl[i] = 0; }
     }
   }
 }
@@ -503,8 +573,10 @@ __global__ void __launch_bounds__(FQ_CNT_NT, 1) fq_count_kernel(const KpcFqLaunc
 
 uint32_t kpc_fq_tile_bytes() { return FQ_TB; }
 // bins per slice: at most 2^15 (one u16 queue entry, a 128 KiB shared-memory table) and at least 128 slices so
-// that the counting kernel has enough CTAs
+// that the counting kernel has enough CTAs; the slice index is cut out of the middle of the key
 int kpc_fq_log_bins(int k) { return 2 * k - 7 < 15 ? 2 * k - 7 : 15; }
+int kpc_fq_lo_bits(int k) { return kpc_fq_log_bins(k) / 2; }
+uint32_t kpc_fq_queue_slack() { return FQ_CHUNK * 512u; }  // padding entries per slice: < one chunk per CTA (<= 2 per SM)
 bool kpc_fq_supported(int k, int content) {
   return (content == KPC_CONTENT_DNA_SS || content == KPC_CONTENT_DNA_DS) && k >= 4 && k <= 12;
 }
@@ -528,7 +600,9 @@ static void launch_partition(const KpcFqLaunch &L, rt_stream s) {
 }
 
 void kpc_fq_partition(const KpcFqLaunch &L, rt_stream s) {
-  if (!kpc_fq_supported(L.k, L.content) || L.n_slices > (uint32_t)FQ_MAXSLICES || L.n_slices < 1)
+  if (!kpc_fq_supported(L.k, L.content) || L.n_slices > (uint32_t)FQ_MAXSLICES || L.n_slices < 1 ||
+      (L.n_slices & (L.n_slices - 1)) || (FQ_BUCKET_ENTRIES / L.n_slices) % FQ_CHUNK || FQ_BUCKET_ENTRIES / L.n_slices < 2 * FQ_CHUNK ||
+      (1u << L.slice_bits) != L.n_slices || L.lo_bits + L.slice_bits > 2 * L.k)
     throw KpcError(KPC_E_STATE, "internal: fast FASTQ path asked for an unsupported configuration");
   const bool ds = L.content == KPC_CONTENT_DNA_DS;
   if (L.k == 12) { if (ds) launch_partition<true, 12>(L, s); else launch_partition<false, 12>(L, s); }

@@ -6,8 +6,9 @@
 //
 //   fq_partition   record framing (Files.FASTQ.iter_se, Files.ml:201-221) + linting (Sequences.ml:41-67) +
 //                  forward / reverse-complement k-mers and min (KMers.ml:357-389), 16 windows per thread with
-//                  SIMD-in-register classification; the canonical keys of a tile are counting-sorted in shared
-//                  memory by their top bits ("slice") and appended, 16 bits per k-mer, to per-slice queues in HBM
+//                  SIMD-in-register classification; every canonical key is appended to a shared-memory bucket of
+//                  its "slice" (middle bits of the key) and whole 32-byte chunks of the buckets are appended,
+//                  16 bits per k-mer, to per-slice queues in HBM (software write-combining)
 //   fq_count       one CTA per slice: the slice of the table (2^15 u32 bins) lives in shared memory, queue entries
 //                  are counted with shared-memory atomics, non-zero bins are added to the global table
 //                  (IntHashFrequencies.add, KMers.ml:107-111)
@@ -35,10 +36,11 @@ struct KpcFqLaunch {
   uint32_t n_tiles;
   // slices and queues
   int log_bins;                    // bins per slice = 1 << log_bins (<= 15)
-  uint32_t n_slices;               // 4^k >> log_bins  (2 .. 512)
+  int lo_bits, slice_bits;         // slice = key bits [lo_bits, lo_bits + slice_bits); bin = the other bits, packed
+  uint32_t n_slices;               // 1 << slice_bits = 4^k >> log_bins  (128 or 512)
   uint16_t *queue;
-  const unsigned long long *qbase; // first entry of every slice's queue (multiple of 8)
-  const uint32_t *qcap;            // capacity of every slice's queue, in entries
+  const unsigned long long *qbase; // first entry of every slice's queue (multiple of 16)
+  const uint32_t *qcap;            // capacity of every slice's queue, in entries (multiple of 16)
   uint32_t *qcursor;               // entries appended so far (may exceed the capacity): zero on entry
   uint32_t *table;                 // the dense 4^k table
 };
@@ -46,5 +48,7 @@ struct KpcFqLaunch {
 uint32_t kpc_fq_tile_bytes();
 bool kpc_fq_supported(int k, int content);
 int kpc_fq_log_bins(int k);
+int kpc_fq_lo_bits(int k);
+uint32_t kpc_fq_queue_slack();
 void kpc_fq_partition(const KpcFqLaunch &L, rt_stream s);
 void kpc_fq_count(const KpcFqLaunch &L, rt_stream s);

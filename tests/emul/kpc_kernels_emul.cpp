@@ -86,6 +86,8 @@ void kpc_k_tiles(const KpcTileLaunch &L, rt_stream) {
 uint32_t kpc_fq_tile_bytes() { return 32768; }
 bool kpc_fq_supported(int, int) { return false; }
 int kpc_fq_log_bins(int) { return 15; }
+int kpc_fq_lo_bits(int) { return 7; }
+uint32_t kpc_fq_queue_slack() { return 0; }
 void kpc_fq_partition(const KpcFqLaunch &, rt_stream) { throw KpcError(KPC_E_STATE, "emulation: no fast FASTQ path"); }
 void kpc_fq_count(const KpcFqLaunch &, rt_stream) { throw KpcError(KPC_E_STATE, "emulation: no fast FASTQ path"); }
 
