@@ -76,6 +76,7 @@ struct FqSmem {
   unsigned long long G;                           // number of '\n' in the stream before the tile
   uint32_t tileq[2];
   uint32_t nbig;
+  uint32_t cnt_next;                              // newline count of the next tile (fq_count_tile)
   uint32_t umax, usum;                            // longest row of the batch (units) and the sum over its rows
   int head;                                       // position of the last '\n' before the tile (-1 .. -16), or -17
   uint16_t nlpos[FQ_MAXSLOTS + 2];
@@ -129,6 +130,46 @@ __device__ __forceinline__ uint32_t nl_mask16(const uint4 &x) {
   return (lo + (hi << 8)) >> 7;
 }
 
+// number of '\n' in the 16-byte vector
+__device__ __forceinline__ uint32_t nl_count16(const uint4 &x) {
+  return __popc(nl_mask(x.x)) + __popc(nl_mask(x.y)) + __popc(nl_mask(x.z)) + __popc(nl_mask(x.w));
+}
+// newline count of a whole tile, one tile ahead of its processing: threads [first, FQ_NT) add their share to *acc
+__device__ __forceinline__ void fq_count_tile(const KpcFqLaunch &p, uint32_t tile, int tid, int first, uint32_t *acc) {
+  const uint64_t t0 = (uint64_t)tile * FQ_TB;
+  const int len = (int)((p.n - t0) < (uint64_t)FQ_TB ? (p.n - t0) : (uint64_t)FQ_TB);
+  uint32_t c = 0;
+  constexpr int NV = FQ_TB / 16;
+  if (len == FQ_TB && first == 32) {  // full tile, 15 warps: all the loads of a thread are in flight together
+    constexpr int ROUNDS = (NV + FQ_NT - 32 - 1) / (FQ_NT - 32);
+    uint4 x[ROUNDS];
+#pragma unroll
+    for (int u = 0; u < ROUNDS; ++u) {
+      const int i = tid - 32 + u * (FQ_NT - 32);
+      x[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < NV) x[u] = ldg_stream(p.data + t0 + 16 * i);
+    }
+#pragma unroll
+    for (int u = 0; u < ROUNDS; ++u) c += nl_count16(x[u]);
+  } else {
+    for (int i = tid - first; 16 * i < len; i += FQ_NT - first) {
+      uint4 x = ldg_stream(p.data + t0 + 16 * i);
+      if (16 * i + 16 > len) {  // bytes past the end read as 0
+        uint32_t *xw = reinterpret_cast<uint32_t *>(&x);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int rem = len - (16 * i + 4 * m);
+          if (rem <= 0) xw[m] = 0u;
+          else if (rem < 4) xw[m] &= (1u << (8 * rem)) - 1u;
+        }
+      }
+      c += nl_count16(x);
+    }
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((tid & 31) == 0 && c) atomicAdd(acc, c);
+}
+
 // slice / bin of a key and back: slice = key bits [lo, lo + sb), bin = the other bits packed together
 __device__ __forceinline__ uint32_t fq_slice_of(uint32_t key, int lo, uint32_t smask) { return (key >> lo) & smask; }
 __device__ __forceinline__ uint32_t fq_bin_of(uint32_t key, int lo, int sb, uint32_t lomask) {
@@ -144,13 +185,15 @@ __device__ __forceinline__ uint32_t fq_key_of(uint32_t slice, uint32_t bin, int 
 // at any of them, which makes the common case one L2 round trip.
 constexpr unsigned long long FQ_ST_AGG = 1ull << 62, FQ_ST_INC = 2ull << 62, FQ_VAL = (1ull << 62) - 1ull;
 constexpr int FQ_LB_ROUNDS = 10;
+// the tile's own count is published one tile ahead of its processing (fq_count_tile), so that by the time a tile
+// looks back every predecessor has published at least its aggregate: nobody waits for anybody
+__device__ __forceinline__ void lookback_publish(unsigned long long *state, uint32_t tile, uint32_t total,
+                                                 unsigned long long g_in) {
+  st_relaxed_u64(state + tile, tile == 0 ? (FQ_ST_INC | (g_in + total)) : (FQ_ST_AGG | (unsigned long long)total));
+}
 __device__ __forceinline__ unsigned long long lookback(unsigned long long *state, uint32_t tile, uint32_t total,
                                                        unsigned long long g_in, int lane) {
-  if (tile == 0) {
-    if (lane == 0) st_relaxed_u64(state, FQ_ST_INC | (g_in + total));
-    return g_in;
-  }
-  if (lane == 0) st_relaxed_u64(state + tile, FQ_ST_AGG | (unsigned long long)total);
+  if (tile == 0) return g_in;
   unsigned long long acc = 0;
   long long j0 = (long long)tile - 1;
   for (;;) {
@@ -284,7 +327,11 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
 #define FQ_T(i) do { if (FQ_PMAP(i) >= 0) { const uint32_t t_ = (uint32_t)clock(); prof[FQ_PMAP(i) < 0 ? 0 : FQ_PMAP(i)] += t_ - tlast; tlast = t_; } } while (0)
 // profile slots: 0 load..sync1 | 1 sync1..sync2 (scan, look-back, newline positions) | 2 sync2..sync4 (rows, units) |
 //                3 classify | 4 copy-out + barrier | 5 append + barrier + reserve
+#if !defined(FQ_PSET) || FQ_PSET == 0
 #define FQ_PMAP(i) ((i) == 1 ? 0 : (i) == 3 ? 1 : (i) == 4 ? 2 : (i) == 5 ? 3 : (i) == 7 ? 4 : (i) == 9 ? 5 : -1)
+#else  // inside "rows": 0 everything up to sync2 | 1 malformed check | 2 row info | 3 reductions | 4 barrier (3) | 5 the rest of the tile
+#define FQ_PMAP(i) ((i) == 3 ? 0 : (i) == 11 ? 1 : (i) == 12 ? 2 : (i) == 15 ? 3 : (i) == 13 ? 4 : (i) == 9 ? 5 : -1)
+#endif
 #else
 #define FQ_T(i) do { } while (0)
 #endif
@@ -314,19 +361,30 @@ __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunc
   if (tid < FQ_MAXSLICES) S.fill[tid] = 0;
   if ((uint32_t)tid < NS) { S.qb16[tid] = (uint32_t)(__ldg(p.qbase + tid) / FQ_CHUNK); S.qcap[tid] = __ldg(p.qcap + tid); }
   if (tid < 48) S.raw[FQ_HALO + FQ_TB + tid] = 0;
-  if (tid == 0) { S.tileq[0] = atomicAdd(p.counters, 1u); S.nbig = 0; S.umax = 0; S.usum = 0; }
+  if (tid == 0) { S.tileq[0] = atomicAdd(p.counters, 1u); S.nbig = 0; S.umax = 0; S.usum = 0; S.cnt_next = 0; }
   const unsigned long long g_in = p.carry_in->s1.count;  // lines before the launch
   __syncthreads();
+  {  // the first tile's count is published here, every later one while the tile before it is processed
+    const uint32_t first_tile = S.tileq[0];
+    if (first_tile < p.n_tiles) fq_count_tile(p, first_tile, tid, 0, &S.cnt_next);
+    __syncthreads();
+    if (tid == 0) {
+      if (first_tile < p.n_tiles) lookback_publish(p.tile_state, first_tile, S.cnt_next, g_in);
+      S.cnt_next = 0;
+      S.tileq[1] = atomicAdd(p.counters, 1u);
+    }
+    __syncthreads();
+  }
 
   for (uint32_t it = 0;; ++it) {
-    const uint32_t tile = S.tileq[it & 1];
+    const uint32_t tile = S.tileq[it & 1], tile_next = S.tileq[(it + 1) & 1];
     if (tile >= p.n_tiles) break;
     const uint64_t t0 = (uint64_t)tile * FQ_TB;
     const int len = (int)((p.n - t0) < (uint64_t)FQ_TB ? (p.n - t0) : (uint64_t)FQ_TB);
 
-    // the tile one grid ahead is pulled into L2 now (whoever claims it finds it there: loads cost an L2 round trip)
+    // the tile two grids ahead is pulled into L2 now: it is counted one tile time from now and processed after two
     if (tid == 0) {
-      const uint64_t pt = (uint64_t)tile + gridDim.x;
+      const uint64_t pt = (uint64_t)tile + 2u * gridDim.x;
       if (pt < p.n_tiles) {
         const uint64_t pb = pt * FQ_TB;
         const uint32_t pn = (uint32_t)((p.n - pb) < (uint64_t)FQ_TB ? (p.n - pb) : (uint64_t)FQ_TB) & ~15u;
@@ -427,6 +485,9 @@ __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunc
       }
     }
 
+    // while warp 0 looks back, the other warps count the newlines of the NEXT tile of this CTA (its bytes are in L2)
+    if (w != 0 && tile_next < p.n_tiles) fq_count_tile(p, tile_next, tid, 32, &S.cnt_next);
+
     // ---- 2./3. lines -> slots -> rows -> units, in batches of FQ_MAXSLOTS lines ------------------------------
     for (uint32_t lo = 0; lo < N + 1u; lo += FQ_MAXSLOTS) {
       if (lo) {
@@ -454,7 +515,13 @@ __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunc
       __syncthreads();  // (2) nlpos[] of the batch, G and head are visible
       FQ_T(3);
       const unsigned long long G = S.G;
-      if (tid == 0) S.nbig = 0;
+      if (tid == 0) {
+        S.nbig = 0;
+        if (lo == 0) {  // the next tile's count goes out one tile ahead of its processing
+          if (tile_next < p.n_tiles) lookback_publish(p.tile_state, tile_next, S.cnt_next, g_in);
+          S.cnt_next = 0;
+        }
+      }
       const uint32_t hi = (N + 1u < lo + FQ_MAXSLOTS) ? N + 1u : lo + FQ_MAXSLOTS;  // slots [lo, hi)
       const uint32_t jrow0 = (uint32_t)((1ull - (G + lo)) & 3ull);                  // first slot (batch relative) on phase 1
       const uint32_t NR = (hi - lo > jrow0) ? (hi - lo - jrow0 + 3u) / 4u : 0u;
@@ -491,12 +558,13 @@ __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunc
         const uint32_t wmax = __reduce_max_sync(0xffffffffu, nunits), wsum = __reduce_add_sync(0xffffffffu, nunits);
         if (lane == 0 && wsum) { atomicMax(&S.umax, wmax); atomicAdd(&S.usum, wsum); }
       }
+      FQ_T(15);
       __syncthreads();  // (3)
+      FQ_T(13);
       const uint32_t UPR = S.umax, usum = S.usum;
       const bool uniform = NR * UPR <= usum + (usum >> 2) + 64u;
       const uint32_t recip = UPR > 1u ? 0xFFFFFFFFu / UPR + 1u : 0u;  // q / UPR = umulhi(q, recip) for q < 2^16, UPR > 1
       uint32_t U = NR * UPR;
-      FQ_T(13);
       if (!uniform) {
         const uint32_t ub = block_excl_scan(nunits, S.wtot_b, U, lane, w);
         if (nunits) {
@@ -664,7 +732,7 @@ __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunc
       }
     }
     if (!claimed && tid == 0) next_tile = atomicAdd(p.counters, 1u);
-    if (tid == 0) { S.tileq[(it + 1) & 1] = next_tile; S.umax = 0; S.usum = 0; }
+    if (tid == 0) { S.tileq[it & 1] = next_tile; S.umax = 0; S.usum = 0; }  // slot of the tile just finished
     __syncthreads();  // the next tile overwrites raw[], nlpos[] and the scan scratch
   }
 #ifdef FQ_PROFILE
