@@ -111,6 +111,10 @@ void *kpc_stream(kpc_ctx *ctx);          /* cudaStream_t the counting kernels ar
 int kpc_sync(kpc_ctx *ctx);
 unsigned long long kpc_kernel_launches(const kpc_ctx *ctx); /* kernels of this library launched so far */
 const char *kpc_backend(void);           /* "cuda" */
+/* measurement aid (bench.py): CUDA-event times of the fast FASTQ kernels since the last read, summed over launches */
+int kpc_profile_enable(kpc_ctx *ctx, int on);
+int kpc_profile_read(kpc_ctx *ctx, double *partition_ms, double *count_ms, unsigned long long *launches,
+                     unsigned long long *bytes);
 /* synthetic single-end FASTQ of the benchmark shape written to device memory (see kpc_synth.h) */
 int kpc_synth_fastq(kpc_ctx *ctx, void *device_out, unsigned long long first_record,
                     unsigned long long n_records, unsigned long long seed);

@@ -41,6 +41,9 @@ PROTOTYPES = {
     "kpc_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "kpc_kernel_launches": (ctypes.c_ulonglong, [ctypes.c_void_p]),
     "kpc_backend": (ctypes.c_char_p, []),
+    "kpc_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "kpc_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                        ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]),
     "kpc_synth_fastq": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_ulonglong,
                                        ctypes.c_ulonglong]),
     "kpc_synth_offset": (ctypes.c_ulonglong, [ctypes.c_ulonglong]),

@@ -141,6 +141,17 @@ class KMerCounter:
     def kernel_launches(self):
         return self._lib.kpc_kernel_launches(self._ctx)
 
+    def profile_enable(self, on=True):
+        """CUDA-event timing of the fast FASTQ kernels (measurement aid of bench.py)."""
+        self._check(self._lib.kpc_profile_enable(self._ctx, 1 if on else 0))
+
+    def profile_read(self):
+        """(partition_ms, count_ms, launches, bytes) summed over the launches since the last read."""
+        a, b = ctypes.c_double(), ctypes.c_double()
+        n, nb = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+        self._check(self._lib.kpc_profile_read(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n), ctypes.byref(nb)))
+        return a.value, b.value, n.value, nb.value
+
     def kmers_counted(self):
         out = ctypes.c_ulonglong()
         self._check(self._lib.kpc_kmers_counted(self._ctx, ctypes.byref(out)))

@@ -5,6 +5,7 @@
 #include <string>
 
 #include "kpc_engine.h"
+#include "kpc_fastq.h"
 #include "kpc_synth.h"
 
 struct kpc_ctx {
@@ -140,6 +141,14 @@ int kpc_sync(kpc_ctx *ctx) {
 }
 unsigned long long kpc_kernel_launches(const kpc_ctx *ctx) { return (ctx && ctx->engine) ? ctx->engine->launches() : 0; }
 const char *kpc_backend(void) { return rt_backend_name(); }
+int kpc_profile_enable(kpc_ctx *ctx, int on) {
+  return guarded(ctx, [&](KpcEngine &) { kpc_fq_timing_enable(on != 0); });
+}
+int kpc_profile_read(kpc_ctx *ctx, double *partition_ms, double *count_ms, unsigned long long *launches,
+                     unsigned long long *bytes) {
+  if (!partition_ms || !count_ms || !launches || !bytes) return KPC_E_ARG;
+  return guarded(ctx, [&](KpcEngine &e) { e.sync(); kpc_fq_timing_read(partition_ms, count_ms, launches, bytes); });
+}
 int kpc_synth_fastq(kpc_ctx *ctx, void *device_out, unsigned long long first_record, unsigned long long n_records,
                     unsigned long long seed) {
   return guarded(ctx, [&](KpcEngine &e) { e.synth_fastq(device_out, first_record, n_records, seed); });

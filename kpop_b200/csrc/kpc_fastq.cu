@@ -23,6 +23,7 @@
 #include <cstdlib>
 
 #include <string>
+#include <vector>
 
 #include "../../include/kpopcount.h"
 #include "kpc_fastq.h"
@@ -116,10 +117,14 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *wtot, 
   uint32_t wex = __shfl_sync(0xffffffffu, tinc - t, w);
   return wex + inc - v;
 }
-// 0x80 in every byte of w that equals '\n' (exact: three operations)
+// 0x80 in every byte of w that equals '\n' (exact: three operations; the two-constant logic ops are written as LOP3 so
+// that ptxas keeps one constant in a uniform register instead of splitting the operation)
 __device__ __forceinline__ uint32_t nl_mask(uint32_t w) {
-  const uint32_t a = ((w ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-  return ~(a | w) & 0x80808080u;
+  uint32_t t, z;
+  asm("lop3.b32 %0, %1, 0x0A0A0A0A, 0x7F7F7F7F, 0x28;" : "=r"(t) : "r"(w));   // (w ^ 0x0A..) & 0x7F..
+  t += 0x7F7F7F7Fu;
+  asm("lop3.b32 %0, %1, %2, 0x80808080, 0x02;" : "=r"(z) : "r"(t), "r"(w));    // ~(t | w) & 0x80..
+  return z;
 }
 // bit i of the result <=> byte i of the 16-byte vector is '\n': the 0x80 flags are gathered with dot products
 __device__ __forceinline__ uint32_t nl_mask16(const uint4 &x) {
@@ -131,8 +136,11 @@ __device__ __forceinline__ uint32_t nl_mask16(const uint4 &x) {
 }
 
 // number of '\n' in the 16-byte vector
-__device__ __forceinline__ uint32_t nl_count16(const uint4 &x) {
-  return __popc(nl_mask(x.x)) + __popc(nl_mask(x.y)) + __popc(nl_mask(x.z)) + __popc(nl_mask(x.w));
+__device__ __forceinline__ uint32_t nl_count16(const uint4 &x) {  // 0x80 * count, summed with dot products
+  uint32_t c = __dp4a(nl_mask(x.x), 0x01010101u, 0u);
+  c = __dp4a(nl_mask(x.y), 0x01010101u, c);
+  c = __dp4a(nl_mask(x.z), 0x01010101u, c);
+  return __dp4a(nl_mask(x.w), 0x01010101u, c) >> 7;
 }
 // newline count of a whole tile, one tile ahead of its processing: threads [first, FQ_NT) add their share to *acc
 __device__ __forceinline__ void fq_count_tile(const KpcFqLaunch &p, uint32_t tile, int tid, int first, uint32_t *acc) {
@@ -806,6 +814,36 @@ bool kpc_fq_supported(int k, int content) {
 
 static cudaStream_t fq_cs(rt_stream s) { return (cudaStream_t)rt_stream_native(s); }
 
+// ---- optional timing: one event triple per launch (before partition, between, after count) -------------------------
+namespace {
+struct FqTiming {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;  // 3 per launch
+  size_t used = 0;              // launches recorded since the last read
+  unsigned long long bytes = 0;
+} g_fqt;
+cudaEvent_t fq_timing_event(size_t i) {
+  while (g_fqt.ev.size() <= i) {
+    cudaEvent_t e;
+    FQ_CUDA_CHECK(cudaEventCreate(&e));
+    g_fqt.ev.push_back(e);
+  }
+  return g_fqt.ev[i];
+}
+}  // namespace
+void kpc_fq_timing_enable(bool on) { g_fqt.on = on; g_fqt.used = 0; g_fqt.bytes = 0; }
+void kpc_fq_timing_read(double *partition_ms, double *count_ms, unsigned long long *launches, unsigned long long *bytes) {
+  double a = 0, b = 0;
+  for (size_t i = 0; i < g_fqt.used; ++i) {
+    float t = 0;
+    FQ_CUDA_CHECK(cudaEventSynchronize(g_fqt.ev[3 * i + 2]));
+    FQ_CUDA_CHECK(cudaEventElapsedTime(&t, g_fqt.ev[3 * i], g_fqt.ev[3 * i + 1])); a += t;
+    FQ_CUDA_CHECK(cudaEventElapsedTime(&t, g_fqt.ev[3 * i + 1], g_fqt.ev[3 * i + 2])); b += t;
+  }
+  *partition_ms = a; *count_ms = b; *launches = g_fqt.used; *bytes = g_fqt.bytes;
+  g_fqt.used = 0; g_fqt.bytes = 0;
+}
+
 template <bool DS, int KT>
 static void launch_partition(const KpcFqLaunch &L, rt_stream s) {
   auto kern = fq_partition_kernel<DS, KT>;
@@ -829,8 +867,10 @@ void kpc_fq_partition(const KpcFqLaunch &L, rt_stream s) {
       (1u << L.slice_bits) != L.n_slices || L.lo_bits + L.slice_bits > 2 * L.k)
     throw KpcError(KPC_E_STATE, "internal: fast FASTQ path asked for an unsupported configuration");
   const bool ds = L.content == KPC_CONTENT_DNA_DS;
+  if (g_fqt.on) FQ_CUDA_CHECK(cudaEventRecord(fq_timing_event(3 * g_fqt.used), fq_cs(s)));
   if (L.k == 12) { if (ds) launch_partition<true, 12>(L, s); else launch_partition<false, 12>(L, s); }
   else { if (ds) launch_partition<true, 0>(L, s); else launch_partition<false, 0>(L, s); }
+  if (g_fqt.on) FQ_CUDA_CHECK(cudaEventRecord(fq_timing_event(3 * g_fqt.used + 1), fq_cs(s)));
 }
 
 void kpc_fq_count(const KpcFqLaunch &L, rt_stream s) {
@@ -843,4 +883,9 @@ void kpc_fq_count(const KpcFqLaunch &L, rt_stream s) {
   if (grid > (long long)L.n_slices) grid = L.n_slices;
   fq_count_kernel<<<(unsigned)grid, FQ_CNT_NT, (size_t)4 << L.log_bins, fq_cs(s)>>>(L);
   FQ_CUDA_CHECK(cudaGetLastError());
+  if (g_fqt.on) {
+    FQ_CUDA_CHECK(cudaEventRecord(fq_timing_event(3 * g_fqt.used + 2), fq_cs(s)));
+    g_fqt.used++;
+    g_fqt.bytes += L.n;
+  }
 }

@@ -52,3 +52,6 @@ int kpc_fq_lo_bits(int k);
 uint32_t kpc_fq_queue_slack();
 void kpc_fq_partition(const KpcFqLaunch &L, rt_stream s);
 void kpc_fq_count(const KpcFqLaunch &L, rt_stream s);
+// optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline figure)
+void kpc_fq_timing_enable(bool on);
+void kpc_fq_timing_read(double *partition_ms, double *count_ms, unsigned long long *launches, unsigned long long *bytes);

@@ -86,10 +86,12 @@ void kpc_k_tiles(const KpcTileLaunch &L, rt_stream) {
 uint32_t kpc_fq_tile_bytes() { return 32768; }
 bool kpc_fq_supported(int, int) { return false; }
 int kpc_fq_log_bins(int) { return 15; }
-int kpc_fq_lo_bits(int) { return 7; }
+int kpc_fq_lo_bits(int) { return 8; }
 uint32_t kpc_fq_queue_slack() { return 0; }
 void kpc_fq_partition(const KpcFqLaunch &, rt_stream) { throw KpcError(KPC_E_STATE, "emulation: no fast FASTQ path"); }
 void kpc_fq_count(const KpcFqLaunch &, rt_stream) { throw KpcError(KPC_E_STATE, "emulation: no fast FASTQ path"); }
+void kpc_fq_timing_enable(bool) {}
+void kpc_fq_timing_read(double *a, double *b, unsigned long long *c, unsigned long long *d) { *a = 0; *b = 0; *c = 0; *d = 0; }
 
 void kpc_k_count_newlines(const uint8_t *d, uint64_t n, unsigned long long *out, rt_stream) {
   unsigned long long c = 0;
