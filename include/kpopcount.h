@@ -66,6 +66,10 @@ const char *kpc_error(const kpc_ctx *ctx);
 /* where the text goes (stdout / open_out fname in bin/KPopCount.ml:27-31).  Must be set before kpc_begin:
  * the label header is written when the first input starts (:33-34) and -L / spill dumps happen while feeding. */
 int kpc_set_sink(kpc_ctx *ctx, kpc_sink_fn sink, void *user);
+/* alternative to a callback: the text is written (device -> host copies included) straight into a caller-owned host
+ * buffer, e.g. a pinned Bigarray; NULL switches back to the callback.  kpc_reset rewinds it. */
+int kpc_set_sink_buffer(kpc_ctx *ctx, void *host_buffer, size_t capacity);
+unsigned long long kpc_sink_buffer_used(const kpc_ctx *ctx);
 
 /* pinned host buffers owned by the context, for zero-copy reads (slot in [0, kpc_staging_slots)).
  * Blocks until the previous kpc_feed from that slot has left the buffer. */

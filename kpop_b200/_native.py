@@ -41,6 +41,8 @@ PROTOTYPES = {
     "kpc_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "kpc_kernel_launches": (ctypes.c_ulonglong, [ctypes.c_void_p]),
     "kpc_backend": (ctypes.c_char_p, []),
+    "kpc_set_sink_buffer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]),
+    "kpc_sink_buffer_used": (ctypes.c_ulonglong, [ctypes.c_void_p]),
     "kpc_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "kpc_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                         ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]),

@@ -141,6 +141,13 @@ class KMerCounter:
     def kernel_launches(self):
         return self._lib.kpc_kernel_launches(self._ctx)
 
+    def set_text_buffer(self, ptr, capacity):
+        """Spectra text goes straight into the host buffer at `ptr` (e.g. a pinned tensor) instead of the callback."""
+        self._check(self._lib.kpc_set_sink_buffer(self._ctx, ctypes.c_void_p(ptr), capacity))
+
+    def text_buffer_used(self):
+        return self._lib.kpc_sink_buffer_used(self._ctx)
+
     def profile_enable(self, on=True):
         """CUDA-event timing of the fast FASTQ kernels (measurement aid of bench.py)."""
         self._check(self._lib.kpc_profile_enable(self._ctx, 1 if on else 0))

@@ -86,6 +86,10 @@ const char *kpc_error(const kpc_ctx *ctx) { return ctx ? ctx->error.c_str() : "n
 int kpc_set_sink(kpc_ctx *ctx, kpc_sink_fn sink, void *user) {
   return guarded(ctx, [&](KpcEngine &e) { e.set_sink(sink, user); });
 }
+int kpc_set_sink_buffer(kpc_ctx *ctx, void *host_buffer, size_t capacity) {
+  return guarded(ctx, [&](KpcEngine &e) { e.set_sink_buffer(host_buffer, capacity); });
+}
+unsigned long long kpc_sink_buffer_used(const kpc_ctx *ctx) { return (ctx && ctx->engine) ? ctx->engine->sink_buffer_used() : 0; }
 int kpc_discard_text(kpc_ctx *ctx, int discard) {
   return guarded(ctx, [&](KpcEngine &e) { e.set_discard_text(discard != 0); });
 }

@@ -199,6 +199,12 @@ void *KpcEngine::staging(int slot, size_t *capacity) {
 // =================================================================================================
 void KpcEngine::emit(const char *p, size_t n) {
   if (!n || discard_text_) return;
+  if (out_buf_) {
+    if (out_used_ + n > out_cap_) throw KpcError(KPC_E_IO, "the sink buffer is too small for the spectra text");
+    memcpy(out_buf_ + out_used_, p, n);
+    out_used_ += n;
+    return;
+  }
   if (!sink_) throw KpcError(KPC_E_STATE, "no sink set (kpc_set_sink)");
   if (sink_(sink_user_, p, n) != 0) throw KpcError(KPC_E_IO, "the output sink reported a failure");
 }
@@ -223,6 +229,13 @@ void KpcEngine::emit_entries(unsigned long long *keys, unsigned long long *count
     const size_t total = (size_t)h_tmp_[8];
     text_bytes_ += total;
     if (discard_text_) continue;  // device-resident benchmarking: the text stays in HBM
+    if (out_buf_) {               // caller-owned host buffer: one copy, straight to its place
+      if (out_used_ + total > out_cap_) throw KpcError(KPC_E_IO, "the sink buffer is too small for the spectra text");
+      rt_d2h(out_buf_ + out_used_, d_text, total, compute_);
+      rt_stream_sync(compute_);
+      out_used_ += total;
+      continue;
+    }
     for (size_t o = 0; o < total; o += h_out_cap_) {
       const size_t c = std::min(h_out_cap_, total - o);
       rt_d2h(h_out_, d_text + o, c, compute_);
@@ -263,6 +276,7 @@ void KpcEngine::reset() {
   rt_stream_sync(copy_);
   header_done_ = false; failed_ = false; rank_base_ = 0; pair_limit_ = -1; complete_pairs_ = -1;
   text_bytes_ = 0;
+  out_used_ = 0;
   buckets_ = pow2_at_least(16, (uint64_t)cfg_.max_results_size);
   if (mode_ == DENSE) {
     rt_memset(dense_lo_, 0, nbins_ * sizeof(uint32_t), compute_);

@@ -31,6 +31,9 @@ class KpcEngine {
 
   void set_sink(kpc_sink_fn fn, void *user) { sink_ = fn; sink_user_ = user; discard_text_ = false; }
   void set_discard_text(bool d) { discard_text_ = d; }
+  // the text goes straight into a caller-owned host buffer (device -> host copies land there, nothing in between)
+  void set_sink_buffer(void *buf, size_t cap) { out_buf_ = (char *)buf; out_cap_ = cap; out_used_ = 0; if (buf) discard_text_ = false; }
+  unsigned long long sink_buffer_used() const { return out_used_; }
   unsigned long long text_bytes() const { return text_bytes_; }
   void reset();
   int staging_slots() const { return kStagingSlots; }
@@ -135,6 +138,8 @@ class KpcEngine {
   kpc_sink_fn sink_ = nullptr;
   void *sink_user_ = nullptr;
   bool discard_text_ = false;
+  char *out_buf_ = nullptr;
+  size_t out_cap_ = 0, out_used_ = 0;
   unsigned long long text_bytes_ = 0;
   bool header_done_ = false;
   bool failed_ = false;

@@ -138,3 +138,25 @@ def test_fast_fastq_malformed_and_traps(oracle_bin, tmp_path):
         else:
             assert rc_o == 2 and rc_f == -3, (i, rc_o, rc_f)  # KPC_E_MALFORMED_FASTQ; stdout holds the header only
             assert out_f == out_o == b"\tx\n", i
+
+
+def test_sink_buffer_matches_callback():
+    """kpc_set_sink_buffer (text written straight into a caller-owned host buffer) gives the bytes of the callback sink."""
+    import ctypes
+    from kpop_b200 import KMerCounter
+    rng = random.Random(77)
+    data = big_fastq(rng, "reads150")
+    with KMerCounter(k=12, label="buf") as kc:
+        kc.begin("single-end"); kc.feed(data, eof=True); kc.end(); kc.finish()
+        want = kc.take_text()
+        buf = ctypes.create_string_buffer(len(want) + 64)
+        kc.reset()
+        kc.set_text_buffer(ctypes.addressof(buf), len(buf))
+        kc.begin("single-end"); kc.feed(data, eof=True); kc.end(); kc.finish()
+        n = kc.text_buffer_used()
+        assert n == len(want) and buf.raw[:n] == want
+        kc.reset()
+        kc.set_text_buffer(ctypes.addressof(buf), 16)   # too small: a clean error, not an overrun
+        kc.begin("single-end"); kc.feed(data, eof=True); kc.end()
+        with pytest.raises(Exception):
+            kc.finish()
