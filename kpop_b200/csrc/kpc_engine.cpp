@@ -1166,16 +1166,19 @@ void KpcEngine::tuple_flush(bool input_done) {
     };
     kpc_sink_fn saved = sink_;
     void *saved_user = sink_user_;
+    char *saved_buf = out_buf_;  // a caller-owned sink buffer receives the final text only
     sink_ = Collect::fn;
     sink_user_ = &lines;
+    out_buf_ = nullptr;
     try {
       emit_entries(ek, ec, n_final);
     } catch (...) {
-      sink_ = saved; sink_user_ = saved_user;
+      sink_ = saved; sink_user_ = saved_user; out_buf_ = saved_buf;
       throw;
     }
     sink_ = saved;
     sink_user_ = saved_user;
+    out_buf_ = saved_buf;
   }
   size_t lp = 0;
   bool quotes_error = false;

@@ -48,3 +48,32 @@ def test_emul_k9_bucket_order(emul_bin, tmp_path, geom):
     rc, out, err = run_cli(emul_bin, materialise(tmp_path, files, argv), env=emul_env(*geom))
     assert rc == code, err.decode(errors="replace")
     assert out.split(b"\n")[: len(head)] == head
+
+
+@pytest.mark.parametrize("label", ["", "all"], ids=["per_record", "one_label"])
+def test_emul_sink_buffer_matches_callback(emul_bin, label):
+    """kpc_set_sink_buffer (include/kpopcount.h): the text written into a caller-owned host buffer equals what the
+    callback sink receives, in -L mode (records dumped from inside feed/end) and in -l mode (one dump at finish)."""
+    import ctypes
+    import subprocess
+    import sys
+    code = r'''
+import ctypes, sys
+sys.path.insert(0, %r)
+from kpop_b200 import _native
+lib = _native.load(%r)
+from kpop_b200 import KMerCounter
+data = b">a x\nACGTTGCANNACGATCGATCGGCTAGCTAGGATCG\nACGT\n>b\nTTTTTTTTGGGGGGGCCCCCCAAAAAAA\n>\nACGTACGTACGT\n>c\nacgtnacgtacgtagctagc\n" * 7
+with KMerCounter(k=5, label=%r, lib=lib) as kc:
+    kc.begin("fasta"); kc.feed(data, eof=True); kc.end(); kc.finish()
+    want = kc.take_text()
+    buf = ctypes.create_string_buffer(len(want) + 8)
+    kc.reset()
+    kc.set_text_buffer(ctypes.addressof(buf), len(buf))
+    kc.begin("fasta"); kc.feed(data, eof=True); kc.end(); kc.finish()
+    n = kc.text_buffer_used()
+    assert n == len(want) and buf.raw[:n] == want and len(want) > 100, (n, len(want))
+print("ok")
+''' % (ROOT, os.path.join(EMUL_DIR, "_build", "libkpopcount_emul.so"), label)
+    p = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0 and p.stdout.strip() == b"ok", p.stderr.decode(errors="replace")
