@@ -98,6 +98,25 @@ __device__ __forceinline__ uint4 ldg_stream(const uint8_t *p) {
                : "l"(p));
   return x;
 }
+// the same load with an L2 eviction policy: the count-ahead pass wants its tile to stay in L2 until the tile is
+// processed (evict_last), the processing pass reads it for the last time (evict_first)
+__device__ __forceinline__ uint4 ldg_stream_hint(const uint8_t *p, unsigned long long policy) {
+  uint4 x;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+               : "l"(p), "l"(policy));
+  return x;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -148,6 +167,7 @@ __device__ __forceinline__ void fq_count_tile(const KpcFqLaunch &p, uint32_t til
   const int len = (int)((p.n - t0) < (uint64_t)FQ_TB ? (p.n - t0) : (uint64_t)FQ_TB);
   uint32_t c = 0;
   constexpr int NV = FQ_TB / 16;
+  const unsigned long long pol_keep = l2_policy_evict_last();
   if (len == FQ_TB && first == 32) {  // full tile, 15 warps: all the loads of a thread are in flight together
     constexpr int ROUNDS = (NV + FQ_NT - 32 - 1) / (FQ_NT - 32);
     uint4 x[ROUNDS];
@@ -155,7 +175,7 @@ __device__ __forceinline__ void fq_count_tile(const KpcFqLaunch &p, uint32_t til
     for (int u = 0; u < ROUNDS; ++u) {
       const int i = tid - 32 + u * (FQ_NT - 32);
       x[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (i < NV) x[u] = ldg_stream(p.data + t0 + 16 * i);
+      if (i < NV) x[u] = ldg_stream_hint(p.data + t0 + 16 * i, pol_keep);
     }
 #pragma unroll
     for (int u = 0; u < ROUNDS; ++u) c += nl_count16(x[u]);
@@ -371,6 +391,7 @@ __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunc
   if (tid < 48) S.raw[FQ_HALO + FQ_TB + tid] = 0;
   if (tid == 0) { S.tileq[0] = atomicAdd(p.counters, 1u); S.nbig = 0; S.umax = 0; S.usum = 0; S.cnt_next = 0; }
   const unsigned long long g_in = p.carry_in->s1.count;  // lines before the launch
+  const unsigned long long pol_last_use = l2_policy_evict_first();
   __syncthreads();
   {  // the first tile's count is published here, every later one while the tile before it is processed
     const uint32_t first_tile = S.tileq[0];
@@ -405,7 +426,7 @@ __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunc
     for (int q = 0; q < FQ_PIECES; ++q) {
       const int off = 16 * (q * FQ_NT + tid);
       uint4 x = make_uint4(0u, 0u, 0u, 0u);
-      if (off < len) x = ldg_stream(p.data + t0 + off);
+      if (off < len) x = ldg_stream_hint(p.data + t0 + off, pol_last_use);
       if (len < FQ_TB && off + 16 > len) {  // last tile: bytes past the end read as 0
         uint32_t *xw = reinterpret_cast<uint32_t *>(&x);
 #pragma unroll
