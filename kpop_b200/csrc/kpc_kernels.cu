@@ -303,7 +303,15 @@ void kpc_k_dense_extract(const uint32_t *lo, const unsigned long long *hi, uint6
 }
 
 // ---- formatter ----
+// to_hex + Printf "%s\t%d\n" (KMers.ml:270-271, bin/KPopCount.ml:46,60): every entry becomes hex(key) TAB decimal(count) LF.
+// A block formats its 2048 entries into shared memory (placed so that shared and global addresses agree mod 16) and
+// copies the text out with 128-bit stores.
 __device__ __forceinline__ int dec_digits(unsigned long long v) {
+  if (v <= 0xFFFFFFFFull) {
+    const uint32_t x = (uint32_t)v;
+    return 1 + (x >= 10u) + (x >= 100u) + (x >= 1000u) + (x >= 10000u) + (x >= 100000u) + (x >= 1000000u) +
+           (x >= 10000000u) + (x >= 100000000u) + (x >= 1000000000u);
+  }
   int d = 1;
   while (v >= 10ull) { v /= 10ull; ++d; }
   return d;
@@ -313,24 +321,76 @@ struct FormatLen {
   int w;
   __device__ unsigned long long operator()(uint64_t i) const { return (unsigned long long)(w + 2 + dec_digits(counts[i])); }
 };
-struct FormatWrite {
-  const unsigned long long *keys, *counts;
-  int w;
-  char *out;
-  __device__ void operator()(uint64_t i, unsigned long long off, unsigned long long l) const {
-    char *o = out + off;
-    unsigned long long key = keys[i];
-    for (int j = w - 1; j >= 0; --j) { o[j] = "0123456789abcdef"[key & 15ull]; key >>= 4; }
-    o[w] = '\t';
-    unsigned long long c = counts[i];
-    int nd = (int)l - w - 2;
-    for (int j = nd - 1; j >= 0; --j) { o[w + 1 + j] = (char)('0' + (int)(c % 10ull)); c /= 10ull; }
-    o[l - 1] = '\n';
+__global__ void __launch_bounds__(SCAN_THREADS)
+    format_scatter_kernel(const unsigned long long *keys, const unsigned long long *counts, int w, char *out, uint64_t n,
+                          const unsigned long long *partial) {
+  extern __shared__ __align__(16) char fmt_stage[];
+  const uint64_t i0 = (uint64_t)blockIdx.x * SCAN_BLK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  unsigned long long c[SCAN_ITEMS];
+  uint32_t l[SCAN_ITEMS];
+  unsigned long long s = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    c[j] = (i0 + j < n) ? counts[i0 + j] : 0ull;
+    l[j] = (i0 + j < n) ? (uint32_t)(w + 2 + dec_digits(c[j])) : 0u;
+    s += l[j];
   }
-};
+  unsigned long long tot;
+  uint32_t off = (uint32_t)block_exclusive_scan(s, &tot);
+  char *g = out + partial[blockIdx.x];
+  const uint32_t skew = (uint32_t)((uintptr_t)g & 15u);
+  char *st = fmt_stage + skew;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    if (i0 + j < n) {
+      char *o = st + off;
+      unsigned long long key = keys[i0 + j];
+      for (int q = w - 1; q >= 0; --q) { o[q] = "0123456789abcdef"[key & 15ull]; key >>= 4; }
+      o[w] = '\t';
+      const int nd = (int)l[j] - w - 2;
+      if (c[j] <= 0xFFFFFFFFull) {
+        uint32_t v = (uint32_t)c[j];
+        for (int q = nd - 1; q >= 0; --q) { const uint32_t d = v / 10u; o[w + 1 + q] = (char)('0' + (v - d * 10u)); v = d; }
+      } else {
+        unsigned long long v = c[j];
+        for (int q = nd - 1; q >= 0; --q) { o[w + 1 + q] = (char)('0' + (int)(v % 10ull)); v /= 10ull; }
+      }
+      o[l[j] - 1] = '\n';
+      off += l[j];
+    }
+  }
+  __syncthreads();
+  const uint32_t total = (uint32_t)tot;
+  const uint32_t head = min(total, (16u - skew) & 15u);
+  if (threadIdx.x < head) g[threadIdx.x] = st[threadIdx.x];
+  const uint32_t nvec = (total - head) >> 4;
+  const uint4 *sv = reinterpret_cast<const uint4 *>(st + head);
+  uint4 *gv = reinterpret_cast<uint4 *>(g + head);
+  for (uint32_t v = threadIdx.x; v < nvec; v += SCAN_THREADS) gv[v] = sv[v];
+  const uint32_t done = head + (nvec << 4);
+  if (threadIdx.x < total - done) g[done + threadIdx.x] = st[done + threadIdx.x];
+}
 void kpc_k_format(const unsigned long long *keys, const unsigned long long *counts, uint64_t n, int hex_width,
                   char *out, unsigned long long *out_len, void *scratch, rt_stream s) {
-  run_scan(FormatLen{counts, hex_width}, FormatWrite{keys, counts, hex_width, out}, n, out_len, scratch, s);
+  unsigned long long *partial = (unsigned long long *)scratch;
+  const uint64_t nb = (n + SCAN_BLK - 1) / SCAN_BLK;
+  if (nb == 0) {
+    CUDA_CHECK(cudaMemsetAsync(out_len, 0, sizeof(unsigned long long), cs(s)));
+    return;
+  }
+  const size_t smem = (size_t)SCAN_BLK * (size_t)(hex_width + 22) + 32;  // 20 decimal digits at most
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(format_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  scan_sums_kernel<<<(unsigned)nb, SCAN_THREADS, 0, cs(s)>>>(FormatLen{counts, hex_width}, n, partial);
+  CUDA_CHECK(cudaGetLastError());
+  scan_partials_kernel<<<1, 1024, 0, cs(s)>>>(partial, nb);
+  CUDA_CHECK(cudaGetLastError());
+  format_scatter_kernel<<<(unsigned)nb, SCAN_THREADS, smem, cs(s)>>>(keys, counts, hex_width, out, n, partial);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemcpyAsync(out_len, partial + nb, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, cs(s)));
 }
 
 // =================================================================================================
