@@ -789,19 +789,27 @@ __global__ void __launch_bounds__(FQ_CNT_NT, 1) fq_count_kernel(const KpcFqLaunc
   const uint32_t lomask = (1u << slo) - 1u;
   const uint32_t nbins = 1u << lb;
   for (uint32_t i = tid; i < nbins; i += FQ_CNT_NT) tbl[i] = 0;
+  // work items: whole slices while they fill complete waves of the grid; the slices of the last, partial wave are cut
+  // into `parts` pieces so that it keeps every SM busy as well (512 slices on 148 SMs: 444 whole + 68 x 2 halves)
+  const uint32_t G = gridDim.x, rem = p.n_slices % G;
+  const uint32_t parts = rem ? (G / rem < 4u ? G / rem : 4u) : 1u;
+  const uint32_t whole = p.n_slices - rem, n_items = whole + rem * parts;
   for (;;) {
     __syncthreads();
     if (tid == 0) s_slice = atomicAdd(p.counters + 1, 1u);
     __syncthreads();
-    const uint32_t b = s_slice;
-    if (b >= p.n_slices) break;
+    const uint32_t item = s_slice;
+    if (item >= n_items) break;
+    const uint32_t b = item < whole ? item : whole + (item - whole) / parts;
+    const uint32_t part = item < whole ? 0u : (item - whole) % parts, nparts = item < whole ? 1u : parts;
     uint32_t cn = p.qcursor[b];
     const uint32_t cap = p.qcap[b];
     if (cn > cap) cn = cap;  // both are multiples of FQ_CHUNK
     if (!cn) continue;
     const uint4 *sv = reinterpret_cast<const uint4 *>(p.queue + p.qbase[b]);
-    const uint32_t nvec = cn >> 3;
-    uint32_t v = tid;
+    const uint32_t nvec_all = cn >> 3;
+    const uint32_t nvec = (uint32_t)((unsigned long long)nvec_all * (part + 1u) / nparts);
+    uint32_t v = (uint32_t)((unsigned long long)nvec_all * part / nparts) + tid;
     for (; v + 3u * FQ_CNT_NT < nvec; v += 4u * FQ_CNT_NT) {
       uint4 x[4];
 #pragma unroll
