@@ -100,7 +100,7 @@ def main():
         all_same = True
         for g in range(n_genomes):
             data, n = synth_genome(g)
-            t_gpu, got = gpu_run(30, "G%d" % g, False, "fasta", data, repeat=2)
+            t_gpu, got = gpu_run(30, "G%d" % g, False, "fasta", data, repeat=4)
             tot_gpu += t_gpu
             tot_km += kmers_of(got)
             tot_bytes += len(data)
