@@ -640,6 +640,9 @@ __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunc
       }
 
       // ---- 4./5. rounds of FQ_NT units ------------------------------------------------------------------------
+#ifdef FQ_X_ROUND_REPS  // experiment: the rounds of every tile run several times (counts are multiplied): marginal cost of a round
+      for (int rep = 0; rep < FQ_X_ROUND_REPS; ++rep)
+#endif
       for (uint32_t q0 = 0; q0 < U; q0 += FQ_NT) {
         uint32_t ok = 0;
         uint32_t hi24 = 0, lo32 = 0, rlo = 0, rhi = 0;
