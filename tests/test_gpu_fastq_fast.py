@@ -160,3 +160,22 @@ def test_sink_buffer_matches_callback():
         kc.begin("single-end"); kc.feed(data, eof=True); kc.end()
         with pytest.raises(Exception):
             kc.finish()
+
+
+def test_profile_hooks_report_the_fast_kernels():
+    """kpc_profile_enable / kpc_profile_read (measurement aid of bench.py): CUDA-event times of the partition and count
+    kernels, summed over the launches since the last read."""
+    import torch
+    from kpop_b200 import KMerCounter
+    rng = random.Random(5)
+    data = big_fastq(rng, "reads150")
+    with KMerCounter(k=12, label="p") as kc:
+        kc.profile_enable(True)
+        dev = torch.zeros(len(data) + 64, dtype=torch.uint8, device="cuda")
+        dev[: len(data)] = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        kc.begin("single-end"); kc.feed_device(dev.data_ptr(), len(data), eof=True); kc.end()
+        part_ms, count_ms, launches, nbytes = kc.profile_read()
+        assert launches >= 1 and part_ms > 0 and count_ms > 0 and 0 < nbytes <= len(data) + 1
+        assert kc.profile_read()[2] == 0   # reading resets
+        kc.profile_enable(False)
+        kc.finish()
