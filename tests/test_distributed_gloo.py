@@ -77,3 +77,44 @@ def test_shard_records_tiles_the_range():
                 assert a == prev and b >= a
                 prev = b
             assert prev == total
+
+
+def _range_worker(rank, world, port, path, tmp):
+    sys.path.insert(0, ROOT)
+    from kpop_b200.distributed import shard_fastq_byte_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, b = shard_fastq_byte_range(path)
+    np.save(os.path.join(tmp, f"range{rank}.npy"), np.array([a, b], dtype=np.int64))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fastq_file_is_cut_at_record_boundaries(tmp_path, world):
+    """Read-chunk sharding of one FASTQ file: the per-rank byte ranges tile the file, every range starts
+    on a line whose index is a multiple of 4 -- also when quality lines start with '@' or '+' -- and the per-range dense
+    tables (CPU checker) add up to the table of the whole file."""
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+    from test_oracle_fastdense import SYNTH, dense_table, fastdense
+    data = subprocess.run([SYNTH, "0", "700", "3"], stdout=subprocess.PIPE, check=True).stdout
+    trap = b"@x\nACGTACGTACGTACGT\n+\n@+@+@+@+@+@+@+@+\n@y\nTTGCACGTACGTAAAA\n+\n+@+@+@+@+@+@+@+@\n"
+    data = trap * 40 + data + trap * 300 + b"@cut\nACGTACGTACGTAC"      # the last record is incomplete
+    path = tmp_path / "reads.fq"
+    path.write_bytes(data)
+    port = 31000 + (os.getpid() % 2000) + world
+    mp.spawn(_range_worker, args=(world, port, str(path), str(tmp_path)), nprocs=world, join=True)
+    ranges = [tuple(int(x) for x in np.load(tmp_path / f"range{r}.npy")) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == len(data)
+    for r in range(world - 1):
+        assert ranges[r][1] == ranges[r + 1][0]
+    lib = fastdense()
+    total = np.zeros(4 ** K, dtype=np.uint64)
+    for a, b in ranges:
+        assert b >= a
+        if 0 < a < len(data):
+            assert data[a - 1:a] == b"\n" and data[:a].count(b"\n") % 4 == 0   # a record starts here
+        total += dense_table(lib, data[a:b], K).astype(np.uint64)
+    assert np.array_equal(total, dense_table(lib, data, K).astype(np.uint64))
+    assert sum(1 for a, b in ranges if b > a) == world   # nobody idles on this input
