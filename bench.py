@@ -336,10 +336,11 @@ def main():
             "unit": "k-mers/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "C3: synthetic 150bp SE FASTQ, seed 3, %d reads (%d B) per GPU, KPopCount -k 12 -l S3 -s, "
-                                   "dense 4^12 table%s" % (R, nbytes, ", NCCL all-reduce of the tables" if world > 1 else ""),
+            "config": {"workload": "%s: synthetic 150bp SE FASTQ, seed 3, %d reads (%d B) per GPU, KPopCount -k 12 -l S3 -s, "
+                                   "dense 4^12 table%s" % ("C3" if R == C3_RECORDS else "C3 shape, other size", R, nbytes,
+                                                           ", NCCL all-reduce of the tables" if world > 1 else ""),
                        "k": K, "records_per_gpu": R, "bytes_per_gpu": int(nbytes), "kmers_total": int(total_kmers),
-                       "l2": "input (10 GB per GPU) is far larger than L2; no flush needed",
+                       "l2": "input (%.1f GB per GPU) is far larger than L2; no flush needed" % (nbytes / 1e9),
                        "spectrum_text_bytes": int(text_bytes)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
