@@ -56,13 +56,41 @@ def parse_args():
 # clocks during the timed region (B200_PROFILING.md recipe)
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML in a thread every 5 ms
+    (nvidia-smi -lms as a fallback when the NVML binding is missing)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread, self.stop_flag = index, [], None, None, False
+        self.sm, self.mx, self.reason_bits = [], [], 0
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self.nv is not None:
+            try:
+                self.mx = [self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)]
+            except Exception:
+                self.mx = []
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -76,6 +104,19 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag = True
+            if self.thread:
+                self.thread.join(timeout=1)
+            nv, bits = self.nv, self.reason_bits
+            names = (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                     ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                     ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                     ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"))
+            reasons = [n for n, attr in names if bits & int(getattr(nv, attr, 0))]
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx[0] if self.mx else None,
+                    "reasons": reasons, "samples": len(sm), "source": "nvml"}
         if self.proc:
             self.proc.terminate()
             try:
@@ -89,7 +130,7 @@ class ClockSampler:
             if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows):
                 reasons.append(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------------------
