@@ -41,12 +41,15 @@ extern __shared__ __align__(16) uint8_t fq_smem_raw[];
 
 namespace {
 
-constexpr int FQ_NT = 512;                        // threads per CTA
+#ifndef FQ_NT_CFG
+#define FQ_NT_CFG 512
+#endif
+constexpr int FQ_NT = FQ_NT_CFG;                  // threads per CTA (a multiple of 32, at least FQ_MAXSLICES)
 constexpr int FQ_NW = FQ_NT / 32;
 constexpr int FQ_W = 16;                          // window-end positions per unit (one thread)
 constexpr int FQ_CTX = 12;                        // context bytes loaded before a unit (>= k - 1)
-constexpr int FQ_TB = 32768;                      // tile bytes
-constexpr int FQ_PIECES = FQ_TB / (16 * FQ_NT);   // 16-byte vectors per thread
+constexpr int FQ_PIECES = 4;                      // 16-byte vectors per thread
+constexpr int FQ_TB = 16 * FQ_PIECES * FQ_NT;     // tile bytes (32 KiB with 512 threads)
 constexpr int FQ_HALO = 16;
 constexpr int FQ_MAXROWS = FQ_NT;                 // sequence lines per batch
 constexpr int FQ_MAXSLOTS = 4 * FQ_NT;            // lines per batch
@@ -59,7 +62,7 @@ constexpr int FQ_BUCKET_ENTRIES = 24576;          // shared-memory bucket space 
 constexpr int FQ_CHUNK = 16;                      // entries per copy-out chunk (32 bytes: one L2 sector)
 constexpr uint16_t FQ_PAD = 0xFFFFu;              // queue entry that pads the last chunk of a CTA (skipped by fq_count)
 static_assert(FQ_PIECES == 4, "the census packs four newline counts into two scans");
-static_assert(FQ_PIECES * FQ_NW == 64, "census scan layout: two warp totals per lane");
+static_assert(FQ_TB + FQ_BIAS < 65536 && FQ_NT % 32 == 0, "positions are 16-bit");
 static_assert(FQ_MAXSLICES <= FQ_NT, "one thread owns one slice");
 
 struct FqBigRow { uint32_t ub, info, n; };
@@ -465,10 +468,10 @@ __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunc
     uint32_t base[FQ_PIECES];
     uint32_t N;
     {
-      constexpr int VPL = FQ_PIECES * FQ_NW / 32;
+      constexpr int VPL = (FQ_PIECES * FQ_NW + 31) / 32;
       uint32_t a[VPL], s = 0;
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) { a[i] = S.wtot_a[VPL * lane + i]; s += a[i]; }
+      for (int i = 0; i < VPL; ++i) { a[i] = VPL * lane + i < FQ_PIECES * FQ_NW ? S.wtot_a[VPL * lane + i] : 0u; s += a[i]; }
       const uint32_t sinc = warp_incl_scan(s, lane);
       N = __shfl_sync(0xffffffffu, sinc, 31);
       const uint32_t sex = sinc - s;
