@@ -59,6 +59,7 @@ constexpr int FQ_MAXBIG = FQ_TB / (FQ_BIGROW * FQ_W) + 2;
 constexpr int FQ_MAXSLICES = 512;
 constexpr int FQ_BIAS = 17;                       // positions are stored + FQ_BIAS (they start at -17)
 constexpr int FQ_BUCKET_ENTRIES = 24576;          // shared-memory bucket space (u16 entries) shared by all slices
+constexpr int FQ_BPAD = 8;                        // entries between two buckets: a stride of cap + 8 entries (28 or 100 words) keeps the owners' 128-bit accesses free of bank conflicts
 constexpr int FQ_CHUNK = 16;                      // entries per copy-out chunk (32 bytes: one L2 sector)
 constexpr uint16_t FQ_PAD = 0xFFFFu;              // queue entry that pads the last chunk of a CTA (skipped by fq_count)
 static_assert(FQ_PIECES == 4, "the census packs four newline counts into two scans");
@@ -68,7 +69,7 @@ static_assert(FQ_MAXSLICES <= FQ_NT, "one thread owns one slice");
 struct FqBigRow { uint32_t ub, info, n; };
 struct FqSmem {
   alignas(16) uint8_t raw[FQ_HALO + FQ_TB + 48];  // raw[16 + i] = tile byte i
-  alignas(16) uint16_t bucket[FQ_BUCKET_ENTRIES + 2 * FQ_CHUNK];  // slice s owns [s * cap, (s + 1) * cap)
+  alignas(16) uint16_t bucket[FQ_BUCKET_ENTRIES + FQ_BPAD * FQ_MAXSLICES + 2 * FQ_CHUNK];  // slice s owns [s * (cap + FQ_BPAD), + cap)
   uint32_t fill[FQ_MAXSLICES];                    // entries in the bucket (may run past cap while appending)
   uint32_t qb16[FQ_MAXSLICES];                    // queue base of the slice / FQ_CHUNK
   uint32_t qcap[FQ_MAXSLICES];
@@ -271,7 +272,7 @@ __device__ __forceinline__ void fq_flush_reserve(FqSmem &S, const KpcFqLaunch &p
     if (f > cap) f = cap;
     uint32_t n = f & ~(uint32_t)(FQ_CHUNK - 1);
     if (final && n < f) {  // the CTA is leaving: pad the last chunk
-      for (uint32_t i = f; i < n + FQ_CHUNK; ++i) S.bucket[tid * cap + i] = FQ_PAD;
+      for (uint32_t i = f; i < n + FQ_CHUNK; ++i) S.bucket[tid * (cap + FQ_BPAD) + i] = FQ_PAD;
       n += FQ_CHUNK;
       f = n;
     }
@@ -284,7 +285,7 @@ __device__ __forceinline__ void fq_flush_copy(FqSmem &S, const KpcFqLaunch &p, i
                                               uint32_t my_g, int lo, int sb, uint32_t lomask) {
   if (!my_n) return;
   const uint32_t qc = S.qcap[tid];
-  uint4 *src = reinterpret_cast<uint4 *>(S.bucket + tid * cap);
+  uint4 *src = reinterpret_cast<uint4 *>(S.bucket + tid * (cap + FQ_BPAD));
   uint4 *dst = reinterpret_cast<uint4 *>(p.queue + (unsigned long long)S.qb16[tid] * FQ_CHUNK + my_g);
   for (uint32_t c = 0; c < my_n; c += FQ_CHUNK) {
     const uint4 v0 = src[c >> 3], v1 = src[(c >> 3) + 1];
@@ -329,7 +330,7 @@ __device__ __forceinline__ void fq_append_k12(uint32_t kk, uint32_t &pending, ui
       "shr.u32 t, %1, 1;\n\t"
       "prmt.b32 en, %1, t, 0x0071;\n\t"
       "cvt.u16.u32 e16, en;\n\t"
-      "mad.lo.u32 ad, o, 24, %4;\n\t"
+      "mad.lo.u32 ad, o, 28, %4;\n\t"             // bucket of the slice: (48 + FQ_BPAD) entries = 112 bytes apart
       "shl.b32 t, pos, 1;\n\t"
       "add.u32 ad, ad, t;\n\t"
       "@q st.shared.u16 [ad], e16;\n\t"
@@ -744,7 +745,7 @@ __global__ void __launch_bounds__(FQ_NT, 2) fq_partition_kernel(const KpcFqLaunc
               const uint32_t sl = fq_slice_of(key, slo, smask);
               const uint32_t pos = atoms_add(s_fill + 4u * sl, 1u);
               if (pos < cap) {
-                sts_u16(s_bucket + 2u * (sl * cap + pos), fq_bin_of(key, slo, sb, lomask));
+                sts_u16(s_bucket + 2u * (sl * (cap + FQ_BPAD) + pos), fq_bin_of(key, slo, sb, lomask));
                 pending ^= bit;
               }
             }
