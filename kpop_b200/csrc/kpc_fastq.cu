@@ -6,18 +6,27 @@
 //   DNAHash*.iteri / iterc     BiOCamLib/lib/KMers.ml:319-349, 357-389   first base most significant, key = min f rc
 //   IntHashFrequencies.add     BiOCamLib/lib/KMers.ml:107-111   count[key] += 1
 //
-// Geometry: a CTA of FQ_NT threads owns one tile of FQ_TB bytes at a time (claimed in stream order).
-//   1. 128-bit loads -> shared memory; the newline census is taken from the registers on the way
-//   2. block scan of the newline counts; the tile's line index base comes from a single-word decoupled look-back
-//   3. every line of the tile gets a slot (start, end, line index mod 4); sequence lines are cut into units of
-//      FQ_W window-end positions; a scan over the rows gives every unit a number
-//   4. one thread per unit: 12 + 16 bytes -> 2-bit codes + validity bits with SIMD-in-register arithmetic,
-//      forward and reverse-complement words, 16 canonical keys in registers
-//   5. software write-combining: every key is appended (one shared-memory atomic) to the bucket of its slice in
-//      shared memory; full 32-byte chunks of a bucket are reserved in the slice's queue in HBM (one global atomic per
-//      slice and round, issued early so that its latency hides behind the next round's k-mer arithmetic) and copied
-//      out with 128-bit stores.  The slice is taken from the MIDDLE bits of the key: min(f, rc) skews the top and
-//      the bottom bases of a canonical k-mer but leaves the central ones uniform, so the buckets fill evenly.
+// Geometry: a CTA of FQ_NT threads owns one tile of FQ_TB bytes at a time (claimed in stream order); DESIGN.md section 5
+// has the measurements behind every choice.
+//   1. 128-bit loads (L2 evict_first) -> shared memory; the newline census is taken from the registers on the way:
+//      three integer operations per word flag the line feeds, dot products (IDP.4A) gather the flags into a 16-bit mask
+//   2. warp scans over packed counts + one cross-warp scan number the line feeds; the number of line feeds BEFORE the
+//      tile comes from a decoupled look-back over one word per tile.  Every CTA counts its NEXT tile one tile ahead (a
+//      second read, L2 evict_last, of a tile that was bulk-prefetched into L2 two grids earlier) and publishes the count
+//      then, so that the look-back never waits for a predecessor
+//   3. every line gets a slot (start, end, line index mod 4): lines 0 and 2 of a record are checked for '@' / '+',
+//      line 1 is a row; rows are cut into units of FQ_W window-end positions, numbered by a division when all rows
+//      have (about) the same length and by a block scan + unit table otherwise
+//   4. one thread per unit: 12 + 16 bytes -> 2-bit codes + "not a base" flags with SIMD-in-register arithmetic and
+//      dot-product gathers, reverse complement of the 28 bases from two BREVs
+//   5. per window: forward and reverse-complement k-mers funnel-shifted to the top of a word, unsigned min, slice and
+//      queue entry by shift / PRMT, one shared-memory atomic + one predicated 16-bit store into the slice's bucket --
+//      15 SASS instructions per k-mer, no branch (fq_append_k12).  Software write-combining: after every round the
+//      thread that owns a slice reserves whole 32-byte chunks of its bucket in the slice's queue in HBM (one global
+//      atomic, issued a round before its result is needed) and copies them out with 128-bit accesses.  The slice is
+//      taken from the MIDDLE bits of the key: min(f, rc) skews the top and the bottom bases of a canonical k-mer but
+//      leaves the central ones uniform, so the buckets fill evenly; a bucket that overflows anyway (skewed input)
+//      sends its keys to the global table with RED.
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
