@@ -179,3 +179,34 @@ def test_profile_hooks_report_the_fast_kernels():
         assert kc.profile_read()[2] == 0   # reading resets
         kc.profile_enable(False)
         kc.finish()
+
+
+@pytest.mark.parametrize("k", [12, 7])
+def test_fast_fastq_paired_end_big(oracle_bin, tmp_path, k):
+    """-p with two large mate files of different record counts (the shorter one cut inside a record): FASTQ.iter_pe
+    (Files.ml:222-250) stops at the last complete pair, which reaches the fast kernel as a line cap (max_lines)."""
+    from test_gpu_parity import GPU_BIN
+    rng = random.Random(4242 + k)
+
+    def mate(n_reads, tag):
+        out = bytearray()
+        for i in range(n_reads):
+            n = rng.choice([150, 150, 151, 100, 36, 250])
+            seq = bytes(rng.choices(b"ACGTNacgt", weights=[30, 30, 30, 30, 1, 2, 2, 2, 2], k=n))
+            out += b"@r%d/%s\n%s\n+\n%s\n" % (i, tag, seq, bytes(rng.choice(b"@+I5#ACGT") for _ in range(n)))
+        return bytes(out)
+
+    m1, m2 = mate(2600, b"1"), mate(2300, b"2")
+    m2 = m2[: len(m2) - 77]   # the last record of mate 2 is incomplete: 2299 complete pairs
+    f1, f2 = tmp_path / "m1.fq", tmp_path / "m2.fq"
+    f1.write_bytes(m1); f2.write_bytes(m2)
+    argv = ["-k", str(k), "-l", "pe", "-p", str(f1), str(f2)]
+    rc_o, out_o, _ = run_cli(oracle_bin, argv)
+    assert rc_o == 0
+    for chunk in (None, "65536"):
+        env = dict(os.environ)
+        if chunk:
+            env["KPC_CHUNK_BYTES"] = chunk
+        rc_g, out_g, err_g = run_cli(GPU_BIN, argv, env=env)
+        assert rc_g == 0, err_g.decode(errors="replace")
+        assert out_g == out_o, f"paired-end k={k} chunk={chunk}"
