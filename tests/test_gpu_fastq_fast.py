@@ -210,3 +210,17 @@ def test_fast_fastq_paired_end_big(oracle_bin, tmp_path, k):
         rc_g, out_g, err_g = run_cli(GPU_BIN, argv, env=env)
         assert rc_g == 0, err_g.decode(errors="replace")
         assert out_g == out_o, f"paired-end k={k} chunk={chunk}"
+
+
+def test_count_fastq_sharded_single_rank(oracle_bin, tmp_path):
+    """distributed.count_fastq_sharded without a process group (one rank owns the whole file): the same bytes as the oracle;
+    the multi-rank cut logic is covered on CPU by tests/test_distributed_gloo.py and on 2 GPUs by tools/mgpu_file_check.py."""
+    from kpop_b200.distributed import count_fastq_sharded, shard_fastq_byte_range
+    rng = random.Random(99)
+    data = big_fastq(rng, "reads150") + b"@cut\nACGTACGTACGTAC"
+    p = tmp_path / "one.fq"
+    p.write_bytes(data)
+    assert shard_fastq_byte_range(str(p)) == (0, len(data))
+    rc_o, out_o, _ = run_cli(oracle_bin, ["-k", "12", "-l", "x", "-s", str(p)])
+    assert rc_o == 0
+    assert count_fastq_sharded(str(p), k=12, label="x", chunk_bytes=100_000) == out_o
