@@ -46,10 +46,14 @@ struct KpcFqLaunch {
 };
 
 uint32_t kpc_fq_tile_bytes();
-bool kpc_fq_supported(int k, int content);
-int kpc_fq_log_bins(int k);
-int kpc_fq_lo_bits(int k);
-uint32_t kpc_fq_queue_slack();
+// bins per slice: at most 2^15 (one u16 queue entry, a 128 KiB shared-memory table) and at least 128 slices so
+// that the counting kernel has enough CTAs; the slice index is cut out of the middle of the key
+inline int kpc_fq_log_bins(int k) { return 2 * k - 7 < 15 ? 2 * k - 7 : 15; }
+inline int kpc_fq_lo_bits(int k) { return k == 12 ? 8 : kpc_fq_log_bins(k) / 2; }  // k = 12: byte-aligned fields (fq_append_k12)
+inline uint32_t kpc_fq_queue_slack() { return 16u * 512u; }  // padding entries per slice: < one chunk per CTA (<= 2 per SM)
+inline bool kpc_fq_supported(int k, int content) {
+  return (content == KPC_CONTENT_DNA_SS || content == KPC_CONTENT_DNA_DS) && k >= 4 && k <= 12;
+}
 void kpc_fq_partition(const KpcFqLaunch &L, rt_stream s);
 void kpc_fq_count(const KpcFqLaunch &L, rt_stream s);
 // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline figure)

@@ -81,17 +81,7 @@ void kpc_k_tiles(const KpcTileLaunch &L, rt_stream) {
   else throw KpcError(KPC_E_ARG, "KPC_EMUL_TILE: unsupported geometry");
 }
 
-// the fast FASTQ pipeline (kpc_fastq.cu) is warp-level CUDA and has no host rendition: the emulated engine
-// always takes the generic tile machine
-uint32_t kpc_fq_tile_bytes() { return 32768; }
-bool kpc_fq_supported(int, int) { return false; }
-int kpc_fq_log_bins(int) { return 15; }
-int kpc_fq_lo_bits(int) { return 8; }
-uint32_t kpc_fq_queue_slack() { return 0; }
-void kpc_fq_partition(const KpcFqLaunch &, rt_stream) { throw KpcError(KPC_E_STATE, "emulation: no fast FASTQ path"); }
-void kpc_fq_count(const KpcFqLaunch &, rt_stream) { throw KpcError(KPC_E_STATE, "emulation: no fast FASTQ path"); }
-void kpc_fq_timing_enable(bool) {}
-void kpc_fq_timing_read(double *a, double *b, unsigned long long *c, unsigned long long *d) { *a = 0; *b = 0; *c = 0; *d = 0; }
+// (the fast FASTQ pipeline is emulated by kpc_fastq_emul.cpp)
 
 void kpc_k_count_newlines(const uint8_t *d, uint64_t n, unsigned long long *out, rt_stream) {
   unsigned long long c = 0;
