@@ -69,12 +69,11 @@ struct FqSmemT {
   uint32_t dummy[32];                             // where the appends of windows that are not valid count (always >= cap)
   uint32_t uinfo[G::MAXUNITS];                    // unit -> first window end (low half) | end of its line (high half)
   uint16_t rowS[G::MAXROWS + 2], rowE[G::MAXROWS + 2];  // first byte / line feed of every sequence line, + FQ_PBIAS
-  uint32_t wtot[32], wbase[32];
+  uint32_t wtot[32], wtot2[64];                   // warp totals: block scans / census of the next tile (two slots)
   FqBigRow big[G::MAXBIG];
   unsigned long long G_;                          // number of '\n' in the stream before the tile
   unsigned long long mbar;                        // completion of the tile's bulk copy
   uint32_t tileq[2];
-  uint32_t N;                                     // '\n' in the tile
   uint32_t nbig;
   uint32_t umax, usum;                            // longest row of the batch (units) and the sum over its rows
   int head;                                       // position of the last '\n' before the tile (-1 .. -16), or -17
@@ -283,10 +282,61 @@ KP_DEV uint32_t fq_classify4(uint32_t wd, uint32_t &nz) {
   return x;
 }
 
+// ---- newline census of one thread's SEG bytes of a tile, straight from global memory (L2) ------------------------------
+// Taken one tile AHEAD of the tile's processing: the masks wait in registers, the tile's line-feed count is published
+// right away, and by the time the tile looks back every predecessor has published its own (nobody waits for anybody).
+template <class G>
+struct FqCensus {
+  uint32_t mlo, mhi;  // bit b <=> byte SEG * tid + b of the tile is '\n'
+  uint32_t rank0;     // line feeds of the tile before this thread's bytes
+};
+template <class G>
+KP_DEV void fq_census_load(const KpcFqLaunch &p, uint32_t tile, int tid, uint4 (&x)[G::VPT]) {
+  const uint64_t t0 = (uint64_t)tile * G::TB;
+  const int len = (int)((p.n - t0) < (uint64_t)G::TB ? (p.n - t0) : (uint64_t)G::TB);
+#pragma unroll
+  for (int c = 0; c < G::VPT; ++c) {
+    const int off = G::SEG * tid + 16 * c;
+    x[c] = make_uint4(0u, 0u, 0u, 0u);
+    if (off < len) x[c] = kp_ldg_stream(p.data + t0 + off);
+    if (len < G::TB && off + 16 > len) {  // last tile: bytes past the end read as 0
+      uint32_t *xw = reinterpret_cast<uint32_t *>(&x[c]);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int rem = len - (off + 4 * m);
+        if (rem <= 0) xw[m] = 0u;
+        else if (rem < 4) xw[m] &= (1u << (8 * rem)) - 1u;
+      }
+    }
+  }
+}
+// masks + warp scan; lane 31 leaves the warp's total in wtot[w]; returns the inclusive count of the thread
+template <class G>
+KP_DEV uint32_t fq_census_masks(const uint4 (&x)[G::VPT], FqCensus<G> &c, uint32_t *wtot, int lane, int w) {
+  uint32_t m16[G::VPT];
+#pragma unroll
+  for (int i = 0; i < G::VPT; ++i) m16[i] = fq_nl_mask16(x[i]);
+  c.mlo = m16[0]; c.mhi = 0;
+  if (G::VPT >= 2) c.mlo |= m16[G::VPT >= 2 ? 1 : 0] << 16;
+  if (G::VPT == 4) c.mhi = m16[G::VPT == 4 ? 2 : 0] | (m16[G::VPT == 4 ? 3 : 0] << 16);
+  const uint32_t cnt = (uint32_t)__popc(c.mlo) + (uint32_t)__popc(c.mhi);
+  const uint32_t inc = fq_warp_incl_scan(cnt, lane);
+  if (lane == 31) wtot[w] = inc;
+  return inc - cnt;
+}
+// after a barrier: exclusive base of the warp and the tile's total from wtot[]
+template <class G>
+KP_DEV uint32_t fq_census_total(const uint32_t *wtot, uint32_t excl_in_warp, FqCensus<G> &c, int lane, int w) {
+  const uint32_t t = lane < G::NW ? wtot[lane] : 0u;
+  const uint32_t tinc = fq_warp_incl_scan(t, lane);
+  c.rank0 = __shfl_sync(0xffffffffu, tinc - t, w) + excl_in_warp;
+  return __shfl_sync(0xffffffffu, tinc, 31);
+}
+
 template <class G, bool DS, int KT>
 KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
   typedef FqSmemT<G> Smem;
-  constexpr int NT = G::NT, NW = G::NW, TB = G::TB, SEG = G::SEG, VPT = G::VPT;
+  constexpr int NT = G::NT, TB = G::TB, SEG = G::SEG, VPT = G::VPT;
   Smem &S = *reinterpret_cast<Smem *>(smem_raw);
   const uint32_t s_fill = kp_smem_addr(S.fill), s_bucket = kp_smem_addr(S.bucket);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -299,7 +349,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
   const uint32_t dummy_off = (uint32_t)(offsetof(Smem, dummy) - offsetof(Smem, fill)) + 4u * (uint32_t)lane;
   FqOwner<G> own;
   bool flush_pending = false;
-  uint32_t next_tile = 0;                                // thread 0: the tile claimed for the next iteration
+  uint32_t next_tile = 0;                                // thread 0: the tile claimed last
 
 #pragma unroll
   for (int i = 0; i < G::SPT; ++i) {
@@ -312,7 +362,6 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
   if (tid < 32) S.dummy[tid] = 0x40000000u;
   if (tid == 0) {
     S.tileq[0] = atomicAdd(p.counters, 1u);
-    S.tileq[1] = 0xffffffffu;
     S.nbig = 0; S.umax = 0; S.usum = 0;
     kp_mbar_init(&S.mbar, 1);
   }
@@ -330,16 +379,40 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
       kp_bulk_load(S.raw + FQ_HALO, p.data + t0, body, &S.mbar);
     }
   };
-  if (tid == 0 && S.tileq[0] < p.n_tiles) start_tile_load(S.tileq[0]);
+
+  // ---- prologue: census of the first tile, claim of the second -----------------------------------------------------------
+  FqCensus<G> cur;        // the tile being processed
+  uint32_t N = 0;         // its line feeds
+  cur.mlo = 0; cur.mhi = 0; cur.rank0 = 0;
+  {
+    const uint32_t tile0 = S.tileq[0];
+    uint32_t excl = 0;
+    if (tile0 < p.n_tiles) {
+      uint4 x[VPT];
+      fq_census_load<G>(p, tile0, tid, x);
+      excl = fq_census_masks<G>(x, cur, S.wtot, lane, w);
+    }
+    if (tid == 0) {
+      S.tileq[1] = tile0 < p.n_tiles ? atomicAdd(p.counters, 1u) : 0xffffffffu;
+      if (tile0 < p.n_tiles) start_tile_load(tile0);
+    }
+    __syncthreads();
+    if (tile0 < p.n_tiles) {
+      N = fq_census_total<G>(S.wtot, excl, cur, lane, w);
+      if (tid == 0) fq_lookback_publish(p.tile_state, tile0, N, g_in);
+    }
+  }
 
   for (uint32_t it = 0;; ++it) {
-    const uint32_t tile = S.tileq[it & 1];
+    const uint32_t tile = S.tileq[it & 1], tile_next = S.tileq[(it + 1) & 1];
     if (tile >= p.n_tiles) break;
     const uint64_t t0 = (uint64_t)tile * TB;
     const int len = (int)((p.n - t0) < (uint64_t)TB ? (p.n - t0) : (uint64_t)TB);
+    const bool have_next = tile_next < p.n_tiles;
+    uint32_t *wtot_next = S.wtot2 + 32 * (it & 1);
     bool claimed = false, loaded_next = false;
 
-    // the tile two grids ahead is pulled into L2 now
+    // the tile two grids ahead is pulled into L2 now: its census is taken one tile time from now
     if (tid == 0) {
       const uint64_t pt = (uint64_t)tile + 2u * gridDim.x;
       if (pt < p.n_tiles) {
@@ -348,90 +421,58 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
         if (pn) kp_prefetch_l2(p.data + pb, pn);
       }
     }
+    // ---- 1. census of the NEXT tile: the loads overlap the wait for this tile's bytes ------------------------------------
+    FqCensus<G> nxt;
+    nxt.mlo = 0; nxt.mhi = 0; nxt.rank0 = 0;
+    uint32_t nxt_excl = 0;
+    uint4 nx[VPT];
+    if (have_next) fq_census_load<G>(p, tile_next, tid, nx);
     kp_mbar_wait(&S.mbar, it);
     if (t0 == 0 && !p.halo_ok && tid < 4) {
       reinterpret_cast<uint32_t *>(S.raw)[tid] = 0x0A0A0A0Au;
       kp_fence_proxy_async();  // a later bulk copy writes these bytes again
     }
+    if (have_next) nxt_excl = fq_census_masks<G>(nx, nxt, wtot_next, lane, w);
 
-    // ---- 1. newline census of the thread's SEG bytes ------------------------------------------------------------------
-    // The VPT vectors of a thread are visited in a rotated order so that the eight threads of a quarter warp hit
-    // eight different bank groups; the rotation is undone on the packed masks.
-    uint32_t mlo = 0, mhi = 0;  // bit b <=> byte SEG * tid + b is '\n'
-    {
-      const int rot = VPT == 4 ? ((tid >> 1) & 3) : (VPT == 2 ? ((tid >> 2) & 1) : 0);
-      uint32_t m16[VPT];
-#pragma unroll
-      for (int c = 0; c < VPT; ++c) {
-        const int cc = (c + rot) & (VPT - 1);
-        const int off = SEG * tid + 16 * cc;
-        uint4 x = *reinterpret_cast<const uint4 *>(S.raw + FQ_HALO + off);
-        if (len < TB && off + 16 > len) {  // last tile: bytes past the end read as 0
-          uint32_t *xw = reinterpret_cast<uint32_t *>(&x);
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int rem = len - (off + 4 * m);
-            if (rem <= 0) xw[m] = 0u;
-            else if (rem < 4) xw[m] &= (1u << (8 * rem)) - 1u;
-          }
-        }
-        m16[c] = fq_nl_mask16(x);
-      }
-      if (VPT == 4) {  // m16[c] belongs to vector (c + rot) & 3: rotate the packed 64-bit mask left by 16 * rot
-        uint32_t a = m16[0] | (m16[1] << 16), b = m16[2] | (m16[3] << 16);
-        if (rot & 2) { const uint32_t t = a; a = b; b = t; }
-        const uint32_t sh = 16u * (uint32_t)(rot & 1);
-        mlo = __funnelshift_l(b, a, sh);
-        mhi = __funnelshift_l(a, b, sh);
-      } else if (VPT == 2) {
-        mlo = rot ? (m16[1] | (m16[0] << 16)) : (m16[0] | (m16[1] << 16));
-      } else {
-        mlo = m16[0];
-      }
-    }
-    const uint32_t cnt = (uint32_t)__popc(mlo) + (uint32_t)__popc(mhi);
-    const uint32_t inc = fq_warp_incl_scan(cnt, lane);
-    if (lane == 31) S.wtot[w] = inc;
-    __syncthreads();  // (1) wtot[] is complete
-
-    // ---- 2. warp 0: tile total, publish, look back; the other warps finish the pending copy-out ----------------------
+    // ---- 2. warp 0 looks back (every predecessor published a tile ago); the other warps finish the pending copy-out ------
     if (w == 0) {
-      const uint32_t t = lane < NW ? S.wtot[lane] : 0u;
-      const uint32_t tinc = fq_warp_incl_scan(t, lane);
-      const uint32_t N = __shfl_sync(0xffffffffu, tinc, 31);
-      if (lane < NW) S.wbase[lane] = tinc - t;
       // the line the tile starts in: where did it begin?
       int head = -17;
       if (lane < 16 && S.raw[15 - lane] == '\n') head = -(lane + 1);
       const unsigned hm = __ballot_sync(0xffffffffu, head != -17);
       if (hm) head = -(__ffs(hm));
-      if (lane == 0) fq_lookback_publish(p.tile_state, tile, N, g_in);
       const unsigned long long g = fq_lookback(p.tile_state, tile, N, g_in, lane);
-      if (lane == 0) { S.G_ = g; S.N = N; S.head = head; }
+      if (lane == 0) { S.G_ = g; S.head = head; }
     }
     if (flush_pending) {
       fq_flush_copy<G>(S, p, own, tid, cap, slo, sb, lomask);
       flush_pending = false;
     }
-    __syncthreads();  // (2) G, N, head, wbase[]; the buckets may be appended to again
+    __syncthreads();  // (2) G, head, wtot_next[]; the buckets may be appended to again
+    uint32_t N_next = 0;
+    if (have_next) {
+      N_next = fq_census_total<G>(wtot_next, nxt_excl, nxt, lane, w);
+      if (tid == 0) fq_lookback_publish(p.tile_state, tile_next, N_next, g_in);
+    }
 
     const unsigned long long Gl = S.G_;
-    const uint32_t N = S.N;
     const int head = S.head;
-    const uint32_t jrow0 = (uint32_t)((1ull - Gl) & 3ull);            // first line of the tile (tile relative) on phase 1
+    const uint32_t G4 = (uint32_t)Gl & 3u;
+    const uint32_t jrow0 = (1u - G4) & 3u;                            // first line of the tile (tile relative) on phase 1
     const uint32_t NRt = N >= jrow0 ? (N - jrow0) / 4u + 1u : 0u;     // sequence lines that touch the tile
-    const uint32_t rank0 = S.wbase[w] + inc - cnt;                    // line feeds of the tile before this thread's bytes
+    // tile lines below jlim are inside max_lines (incomplete last record, -p cap)
+    const uint32_t jlim = p.max_lines <= Gl ? 0u : (p.max_lines - Gl < 0x7fffffffull ? (uint32_t)(p.max_lines - Gl) : 0x7fffffffu);
 
     // ---- 3./4. lines -> rows -> units, in batches of MAXROWS rows -------------------------------------------------------
     for (uint32_t rb = 0; rb == 0 || rb < NRt; rb += G::MAXROWS) {
       if (rb) __syncthreads();  // the previous batch is done with rowS[] / rowE[] / uinfo[]
-      const uint32_t nrows = NRt - rb < (uint32_t)G::MAXROWS ? NRt - rb : (uint32_t)G::MAXROWS;  // NRt == 0: wraps, unused
+      const uint32_t nrows = NRt - rb < (uint32_t)G::MAXROWS ? NRt - rb : (uint32_t)G::MAXROWS;
       if (tid == 0) {
         S.nbig = 0; S.umax = 0; S.usum = 0;
         if (rb == 0) {
           // a line that starts exactly with the tile: tag.[0] <> '@' || tmp.[0] <> '+' (Files.ml:213)
-          if (head == -1 && len > 0 && (Gl & 1ull) == 0ull && Gl < p.max_lines) {
-            if (S.raw[FQ_HALO] != ((Gl & 3ull) == 0ull ? '@' : '+')) atomicMin(p.err_line, Gl);
+          if (head == -1 && len > 0 && (G4 & 1u) == 0u && jlim > 0u) {
+            if (S.raw[FQ_HALO] != (G4 == 0u ? '@' : '+')) atomicMin(p.err_line, Gl);
           }
           if (jrow0 == 0u && NRt) S.rowS[0] = (uint16_t)(head + 1 + FQ_PBIAS);  // the tile starts inside a sequence line
         }
@@ -442,24 +483,23 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
         }
       }
       {
-        uint32_t a = mlo, b = mhi, j = rank0;
+        uint32_t a = cur.mlo, b = cur.mhi, j = cur.rank0;
         while (a | b) {
           uint32_t bitpos;
           if (a) { bitpos = (uint32_t)__ffs(a) - 1u; a &= a - 1u; }
           else { bitpos = 32u + (uint32_t)__ffs(b) - 1u; b &= b - 1u; }
           const int pos = SEG * tid + (int)bitpos;           // line feed at the end of tile line j
-          if (rb == 0) {
-            // the line that starts after it: an empty tag / '+' line raises as well (the byte is then '\n')
-            const unsigned long long L1 = Gl + j + 1ull;
-            if ((L1 & 1ull) == 0ull && L1 < p.max_lines && pos + 1 < len) {
-              if (S.raw[FQ_HALO + pos + 1] != ((L1 & 3ull) == 0ull ? '@' : '+')) atomicMin(p.err_line, L1);
+          const uint32_t ph1 = (G4 + j + 1u) & 3u;           // phase of the line that starts after it
+          if ((ph1 & 1u) == 0u) {
+            // header / '+' line: an empty one raises as well (the byte is then '\n')
+            if (rb == 0 && j + 1u < jlim && pos + 1 < len) {
+              if (S.raw[FQ_HALO + pos + 1] != (ph1 == 0u ? '@' : '+')) atomicMin(p.err_line, Gl + j + 1ull);
             }
-          }
-          if (j >= jrow0 && ((j - jrow0) & 3u) == 0u) {      // line j is a sequence line: it ends here
-            const uint32_t r = (j - jrow0) / 4u - rb;
-            if (r < (uint32_t)G::MAXROWS) S.rowE[r] = (uint16_t)(pos + FQ_PBIAS);
-          }
-          if (j + 1u >= jrow0 && ((j + 1u - jrow0) & 3u) == 0u) {  // line j + 1 is a sequence line: it starts after it
+            if (ph1 == 2u) {                                 // line j is a sequence line: it ends here
+              const uint32_t r = (j - jrow0) / 4u - rb;
+              if (r < (uint32_t)G::MAXROWS) S.rowE[r] = (uint16_t)(pos + FQ_PBIAS);
+            }
+          } else if (ph1 == 1u) {                            // line j + 1 is a sequence line: it starts after the line feed
             const uint32_t r = (j + 1u - jrow0) / 4u - rb;
             if (r < (uint32_t)G::MAXROWS) S.rowS[r] = (uint16_t)(pos + 1 + FQ_PBIAS);
           }
@@ -468,13 +508,11 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
       }
       __syncthreads();  // (3) rowS[] / rowE[] of the batch
 
-      // rows below max_lines are live (incomplete last record, -p cap)
       uint32_t nunits = 0, rinfo = 0;
       if ((uint32_t)tid < nrows && NRt) {
-        const unsigned long long L = Gl + jrow0 + 4ull * (rb + (uint32_t)tid);
         const int st = (int)S.rowS[tid] - FQ_PBIAS, e = (int)S.rowE[tid] - FQ_PBIAS;
         const int a = st + k - 1 > 0 ? st + k - 1 : 0;  // first window end: line start + k - 1, inside the tile
-        if (L < p.max_lines && e > a) {
+        if (jrow0 + 4u * (rb + (uint32_t)tid) < jlim && e > a) {
           nunits = (uint32_t)(e - a + FQ_W - 1) / FQ_W;
           rinfo = (uint32_t)a | ((uint32_t)e << 16);
         }
@@ -492,7 +530,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
       const uint32_t recip = UPR > 1u ? 0xFFFFFFFFu / UPR + 1u : 0u;  // q / UPR = umulhi(q, recip) for q < 2^16, UPR > 1
       uint32_t U = NR * UPR;
       if (!uniform) {
-        const uint32_t ub = fq_block_excl_scan<NW>(nunits, S.wtot, U, lane, w);
+        const uint32_t ub = fq_block_excl_scan<G::NW>(nunits, S.wtot, U, lane, w);
         if (nunits) {
           if (nunits <= (uint32_t)FQ_BIGROW) {
             for (uint32_t u = 0; u < nunits; ++u) S.uinfo[ub + u] = rinfo + u * FQ_W;
@@ -518,17 +556,14 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
         KpcStreamCarry co;
         co.s1.count = Gl + N;
         co.s1.last_hdr = 0;
-        // position of the last line feed of the tile (or of the halo)
-        int plast = head;
+        int plast = head;  // position of the last line feed of the tile (or of the halo)
         if (N) {
-          // the thread-local masks are not visible here: find it in the bytes (only once per launch)
           plast = len - 1;
           while (plast >= 0 && S.raw[FQ_HALO + plast] != '\n') --plast;
         }
         co.s1.last_nl = N ? p.abs_base + t0 + (uint64_t)plast + 1u : p.carry_in->s1.last_nl;
         co.kc.syms = 0; co.kc.n = 0; co.kc.closed = 1;
-        const unsigned long long L = Gl + N;
-        if ((L & 3ull) == 1ull && L < p.max_lines) {
+        if (((G4 + N) & 3u) == 1u && N < jlim) {
           for (int pos = len - 1; pos > plast && pos >= -FQ_HALO && co.kc.n < (uint32_t)(k - 1); --pos) {
             const uint8_t sym = kpc_classify_dna(S.raw[FQ_HALO + pos]);
             if (sym == KPC_CLS_BREAK) break;
@@ -544,10 +579,10 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
       // ---- 5. rounds of NT units ------------------------------------------------------------------------------------------
       for (uint32_t q0 = 0; q0 < U; q0 += NT) {
         const bool last_round = last_batch && q0 + NT >= U;
-        // the next tile is claimed as late as possible (tiles publish in claim order: an early claim makes every later
-        // tile wait for this CTA), but early enough for the atomic to return before the bulk copy is started
+        // the tile after the next one is claimed late (tiles publish in claim order: an early claim would make every
+        // later tile wait for this CTA), but early enough for the atomic to return before the tile ends
         if (last_round && !claimed) {
-          if (tid == 0) next_tile = atomicAdd(p.counters, 1u);
+          if (tid == 0) next_tile = have_next ? atomicAdd(p.counters, 1u) : 0xffffffffu;
           claimed = true;
         }
         uint32_t ok = 0;
@@ -557,10 +592,9 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
         if (q < U) {
           if (uniform) {
             const uint32_t r = UPR == 1u ? q : __umulhi(q, recip), u = q - r * UPR;
-            const unsigned long long L = Gl + jrow0 + 4ull * (rb + r);
             const int st = (int)S.rowS[r] - FQ_PBIAS, e = (int)S.rowE[r] - FQ_PBIAS;
             const int a = (st + k - 1 > 0 ? st + k - 1 : 0) + (int)(u * FQ_W);
-            if (L < p.max_lines && a < e) info = (uint32_t)a | ((uint32_t)e << 16);
+            if (jrow0 + 4u * (rb + r) < jlim && a < e) info = (uint32_t)a | ((uint32_t)e << 16);
           } else {
             info = S.uinfo[q];
           }
@@ -618,8 +652,8 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
         __syncthreads();      // (B) the buckets may be appended to again; raw[] has been read for the last time in this round
         if (last_round) {     // nothing reads the tile bytes any more: the next tile may land on them
           if (tid == 0) {
-            S.tileq[(it + 1) & 1] = next_tile;
-            if (next_tile < p.n_tiles) start_tile_load(next_tile);
+            S.tileq[it & 1] = next_tile;
+            if (have_next) start_tile_load(tile_next);
           }
           loaded_next = true;
         }
@@ -665,11 +699,13 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
     if (!loaded_next) {
       __syncthreads();  // every thread is done with raw[]
       if (tid == 0) {
-        if (!claimed) next_tile = atomicAdd(p.counters, 1u);
-        S.tileq[(it + 1) & 1] = next_tile;
-        if (next_tile < p.n_tiles) start_tile_load(next_tile);
+        if (!claimed) next_tile = have_next ? atomicAdd(p.counters, 1u) : 0xffffffffu;
+        S.tileq[it & 1] = next_tile;
+        if (have_next) start_tile_load(tile_next);
       }
     }
+    cur = nxt;
+    N = N_next;
     __syncthreads();  // tileq[], and rowS[] / rowE[] / the scan scratch are free for the next tile
   }
   // the CTA leaves: everything still in the buckets goes out, the last chunk of every slice padded

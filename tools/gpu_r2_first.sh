@@ -12,7 +12,7 @@ for tool in memcheck synccheck; do
   rm -f gpurun_out/sanitizer_$tool.full
   echo "== $tool"; tail -n 4 gpurun_out/sanitizer_$tool.log
 done
-( timeout 600 python -m pytest tests/test_gpu_fastq_fast.py -x -q 2>&1 | tail -n 30 ) > gpurun_out/t_fast.log
+( timeout 900 python -m pytest tests/test_gpu_fastq_fast.py tests/test_gpu_parity.py -x -q 2>&1 | tail -n 30 ) > gpurun_out/t_fast.log
 tail -n 4 gpurun_out/t_fast.log
 ( timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e 2>&1 | tail -n 3 ) > gpurun_out/bench_quick.log
 grep -o '"value": [0-9.e+]*\|"ms_per_step": [0-9.]*\|"launch_ms": [0-9.]*\|"count_ms_per_step": [0-9.]*\|"frac": [0-9.]*' gpurun_out/bench_quick.log | head -n 8
