@@ -565,11 +565,14 @@ void KpcEngine::fq_ensure(size_t len) {
   // every byte yields at most one k-mer (FASTQ of 150-base reads has ~0.45) and slices are cut out of the middle
   // of the key, where canonical k-mers of uniform reads are uniform: capacities are 1.25 k-mers per byte spread
   // evenly, plus the padding the CTAs leave behind; anything beyond is counted in place by the kernel.
+  // (KPC_FQ_QUEUE_PERMILLE / KPC_FQ_QUEUE_SLACK: test knobs that make the queues overflow on small inputs)
+  const double fq_queue_factor = (double)env_size("KPC_FQ_QUEUE_PERMILLE", 1250) / 1000.0;
+  const unsigned long long fq_queue_slack = env_size("KPC_FQ_QUEUE_SLACK", kpc_fq_queue_slack());
   std::vector<unsigned long long> base(fq_slices_);
   std::vector<uint32_t> cap(fq_slices_);
   unsigned long long total = 0;
   for (uint32_t b = 0; b < fq_slices_; ++b) {
-    unsigned long long c = (unsigned long long)((double)fq_alloc_len_ * 1.25 / fq_slices_) + kpc_fq_queue_slack();
+    unsigned long long c = (unsigned long long)((double)fq_alloc_len_ * fq_queue_factor / fq_slices_) + fq_queue_slack;
     c = (c + 15) & ~15ull;
     if (c > 0xfffffff0ull) c = 0xfffffff0ull;
     base[b] = total;

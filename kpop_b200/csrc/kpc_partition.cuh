@@ -35,6 +35,13 @@
 #include "kpc_fastq.h"
 #include "kpc_simt.h"
 
+// tuning switches (defaults = what measured best on a B200; tools/gpu_define_variants.sh rebuilds with -D overrides)
+#ifndef FQ_APPEND_GROUP
+#define FQ_APPEND_GROUP 4   // shared-memory atomics issued back to back per group of windows (1, 2 or 4)
+#endif
+#ifndef FQ_L2HINTS
+#define FQ_L2HINTS 1        // census loads evict_last, the tile's bulk copy evict_first
+#endif
 constexpr int FQ_W = 16;                          // window-end positions per unit (one thread)
 constexpr int FQ_CTX = 12;                        // context bytes loaded before a unit (>= k - 1)
 constexpr int FQ_HALO = 16;
@@ -66,17 +73,17 @@ struct FqSmemT {
   alignas(128) uint8_t raw[FQ_HALO + G::TB + 48];  // raw[16 + i] = tile byte i
   alignas(16) uint16_t bucket[FQ_BUCKET_ENTRIES + FQ_BPAD * FQ_MAXSLICES + 2 * FQ_CHUNK];  // slice s owns [s * (cap + FQ_BPAD), + cap)
   uint32_t fill[FQ_MAXSLICES];                    // entries in the bucket (may run past cap while appending)
-  uint32_t dummy[32];                             // where the appends of windows that are not valid count (always >= cap)
   uint32_t uinfo[G::MAXUNITS];                    // unit -> first window end (low half) | end of its line (high half)
   uint16_t rowS[G::MAXROWS + 2], rowE[G::MAXROWS + 2];  // first byte / line feed of every sequence line, + FQ_PBIAS
   uint32_t wtot[32], wtot2[64];                   // warp totals: block scans / census of the next tile (two slots)
   FqBigRow big[G::MAXBIG];
+  struct alignas(16) { int head; uint32_t jrow0, NRt, jlim; } ti;  // framing constants of the tile (warp 0 -> everybody)
   unsigned long long G_;                          // number of '\n' in the stream before the tile
   unsigned long long mbar;                        // completion of the tile's bulk copy
   uint32_t tileq[2];
   uint32_t nbig;
   uint32_t umax, usum;                            // longest row of the batch (units) and the sum over its rows
-  int head;                                       // position of the last '\n' before the tile (-1 .. -16), or -17
+  uint32_t recip[65];                             // 2^32 / u + 1 for u = 2 .. 64 (q / u = umulhi(q, recip[u]), q < 2^16)
 };
 
 KP_DEV uint32_t fq_warp_incl_scan(uint32_t v, int lane) {
@@ -162,11 +169,11 @@ KP_DEV unsigned long long fq_lookback(unsigned long long *state, uint32_t tile, 
       if (done || stale) continue;
       const unsigned inc_mask = __ballot_sync(0xffffffffu, (v[i] >> 62) == 2ull);
       const unsigned inv_mask = __ballot_sync(0xffffffffu, (v[i] >> 62) == 0ull);
-      const int first = inc_mask ? (__ffs(inc_mask) - 1) : 32;
-      const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
+      const int first_inc = inc_mask ? (__ffs(inc_mask) - 1) : 32;
+      const unsigned need = first_inc >= 31 ? 0xffffffffu : ((2u << first_inc) - 1u);
       if (inv_mask & need) { stale = true; continue; }  // a predecessor has not published yet: reload from here
       part += ((need >> lane) & 1u) ? (v[i] & FQ_VAL) : 0ull;
-      if (first < 32) done = true; else j0 -= 32;
+      if (first_inc < 32) done = true; else j0 -= 32;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -198,18 +205,16 @@ KP_DEV void fq_flush_reserve(FqSmemT<G> &S, const KpcFqLaunch &p, FqOwner<G> &ow
     if (s < NS) {
       uint32_t f = S.fill[s];
       if (f > cap) f = cap;
-      uint32_t n = f & ~(uint32_t)(FQ_CHUNK - 1);
-      if (final && n < f) {  // the CTA is leaving: pad the last chunk
-        for (uint32_t e = f; e < n + FQ_CHUNK; ++e) S.bucket[s * (cap + FQ_BPAD) + e] = FQ_PAD;
-        n += FQ_CHUNK;
-        f = n;
-      }
-      S.fill[s] = f - n;
+      // whole chunks; the CTA is leaving: the last chunk goes out as it is (the entries behind the fill are FQ_PAD)
+      const uint32_t n = final ? (f + FQ_CHUNK - 1u) & ~(uint32_t)(FQ_CHUNK - 1) : f & ~(uint32_t)(FQ_CHUNK - 1);
+      S.fill[s] = f > n ? f - n : 0u;
       own.n[i] = n;
       if (n) own.g[i] = atomicAdd(p.qcursor + s, n);
     }
   }
 }
+// Invariant between rounds: every bucket entry at or behind the slice's fill is FQ_PAD (windows that are not valid take
+// a position but store nothing, so their positions must already read as padding).
 template <class G>
 KP_DEV void fq_flush_copy(FqSmemT<G> &S, const KpcFqLaunch &p, const FqOwner<G> &own, int tid, uint32_t cap, int lo, int sb,
                           uint32_t lomask) {
@@ -221,6 +226,10 @@ KP_DEV void fq_flush_copy(FqSmemT<G> &S, const KpcFqLaunch &p, const FqOwner<G> 
     const uint32_t qc = own.qcap[i];
     uint4 *src = reinterpret_cast<uint4 *>(S.bucket + s * (cap + FQ_BPAD));
     uint4 *dst = reinterpret_cast<uint4 *>(p.queue + (unsigned long long)own.qb16[i] * FQ_CHUNK + my_g);
+    const uint4 pad4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    // the remainder (< one chunk) moves to the front
+    uint4 r0 = pad4, r1 = pad4;
+    if (my_n < cap) { r0 = src[my_n >> 3]; r1 = src[(my_n >> 3) + 1]; }
     for (uint32_t c = 0; c < my_n; c += FQ_CHUNK) {
       const uint4 v0 = src[c >> 3], v1 = src[(c >> 3) + 1];
       if (my_g + c + FQ_CHUNK <= qc) {
@@ -234,12 +243,12 @@ KP_DEV void fq_flush_copy(FqSmemT<G> &S, const KpcFqLaunch &p, const FqOwner<G> 
           if (en != FQ_PAD) atomicAdd(p.table + fq_key_of(s, en, lo, sb, lomask), 1u);
         }
       }
+      src[c >> 3] = pad4;  // what has been copied reads as padding again
+      src[(c >> 3) + 1] = pad4;
     }
-    if (my_n < cap) {
-      const uint4 r0 = src[my_n >> 3], r1 = src[(my_n >> 3) + 1];
-      src[0] = r0;
-      src[1] = r1;
-    }
+    if (my_n < cap) { src[my_n >> 3] = pad4; src[(my_n >> 3) + 1] = pad4; }
+    src[0] = r0;
+    src[1] = r1;
   }
 }
 
@@ -247,24 +256,43 @@ KP_DEV void fq_flush_copy(FqSmemT<G> &S, const KpcFqLaunch &p, const FqOwner<G> 
 // kk holds the canonical k-mer in its TOP 2k bits (the bits below are ignored).  `ok & bit` says whether the window is
 // valid; the bit is cleared in `pending` once the key sits in its bucket.  k = 12: slice = key bits [8, 17), the queue
 // entry is key[0, 8) | key[17, 24) << 8 (one PRMT); everything is predicated, there is no branch.
-template <class SmemT>
-KP_DEV void fq_append_k12(SmemT &S, uint32_t kk, uint32_t &pending, uint32_t bit, uint32_t ok, uint32_t dummy_off) {
-  const bool valid = (ok & bit) != 0u;
-  const uint32_t sl4 = (kk >> 14) & 0x7FCu;                       // 4 * slice
-  // windows that are not valid count into per-lane dummy counters (kept >= 48) instead of branching
-  uint32_t *ctr = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(S.fill) + (valid ? sl4 : dummy_off));
-  const uint32_t pos = atomicAdd(ctr, 1u);
-  const uint32_t en = __byte_perm(kk, kk >> 1, 0x0071u);          // key[0, 8) | key[17, 24) << 8
-  if (pos < 48u) {
-    *reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(S.bucket) + sl4 * 28u + pos * 2u) = (uint16_t)en;
-    pending ^= bit;
-  }
-}
+// (moved below fq_top_word)
 // top 32 bits of (hi:lo) << s, 0 <= s < 64
 KP_DEV uint32_t fq_top_word(uint32_t hi, uint32_t lo, int s) {
   if (s >= 32) return lo << (s - 32);
   if (s == 0) return hi;
   return __funnelshift_l(lo, hi, s);
+}
+
+// Four windows jw0 .. jw0 + 3 of a unit, k = 12: the four shared-memory atomics are issued together so that their
+// latencies overlap.  kk holds the canonical k-mer in its TOP 24 bits (the bits below are ignored): slice = key bits
+// [8, 17), the queue entry is key[0, 8) | key[17, 24) << 8 (one PRMT).  A window that is not valid takes a position in
+// some bucket like any other but stores nothing there: the position keeps its FQ_PAD (see fq_flush_copy).  The bit of
+// a valid window is cleared in `pending` once the key sits in its bucket.
+template <bool DS, class SmemT>
+KP_DEV void fq_append4_k12(SmemT &S, uint32_t hi24, uint32_t lo32, uint32_t rhi, uint32_t rlo, int jw0, uint32_t ok,
+                           uint32_t &pending) {
+  constexpr int GR = FQ_APPEND_GROUP;
+  uint32_t kk[GR], sl4[GR], pos[GR];
+#pragma unroll
+  for (int i = 0; i < GR; ++i) {
+    const int jw = jw0 + i;
+    kk[i] = fq_top_word(hi24, lo32, 10 + 2 * jw);
+    if (DS) kk[i] = kp_umin(kk[i], fq_top_word(rhi, rlo, 38 - 2 * jw));
+    sl4[i] = (kk[i] >> 14) & 0x7FCu;                              // 4 * slice
+  }
+#pragma unroll
+  for (int i = 0; i < GR; ++i)
+    pos[i] = atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(S.fill) + sl4[i]), 1u);
+#pragma unroll
+  for (int i = 0; i < GR; ++i) {
+    const uint32_t bit = 1u << (FQ_W - 1 - (jw0 + i));
+    const uint32_t en = __byte_perm(kk[i], kk[i] >> 1, 0x0071u);  // key[0, 8) | key[17, 24) << 8
+    if ((ok & bit) != 0u && pos[i] < 48u) {
+      *reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(S.bucket) + sl4[i] * 28u + pos[i] * 2u) = (uint16_t)en;
+      pending ^= bit;
+    }
+  }
 }
 
 // Sequences.ml:52-58 + KMers.ml:272-277 on four bytes at once: x = (byte >> 1) & 3 maps A C T G (either case) to
@@ -285,28 +313,28 @@ KP_DEV uint32_t fq_classify4(uint32_t wd, uint32_t &nz) {
 // ---- newline census of one thread's SEG bytes of a tile, straight from global memory (L2) ------------------------------
 // Taken one tile AHEAD of the tile's processing: the masks wait in registers, the tile's line-feed count is published
 // right away, and by the time the tile looks back every predecessor has published its own (nobody waits for anybody).
+KP_DEV uint32_t fq_keep_bytes(uint32_t w, int n) {  // the first n bytes of the word, the others zero
+  return n <= 0 ? 0u : (n < 4 ? w & ((1u << (8 * n)) - 1u) : w);
+}
 template <class G>
 struct FqCensus {
   uint32_t mlo, mhi;  // bit b <=> byte SEG * tid + b of the tile is '\n'
   uint32_t rank0;     // line feeds of the tile before this thread's bytes
 };
 template <class G>
-KP_DEV void fq_census_load(const KpcFqLaunch &p, uint32_t tile, int tid, uint4 (&x)[G::VPT]) {
+KP_DEV void fq_census_load(const KpcFqLaunch &p, uint32_t tile, int tid, unsigned long long policy, uint4 (&x)[G::VPT]) {
   const uint64_t t0 = (uint64_t)tile * G::TB;
   const int len = (int)((p.n - t0) < (uint64_t)G::TB ? (p.n - t0) : (uint64_t)G::TB);
 #pragma unroll
   for (int c = 0; c < G::VPT; ++c) {
     const int off = G::SEG * tid + 16 * c;
     x[c] = make_uint4(0u, 0u, 0u, 0u);
-    if (off < len) x[c] = kp_ldg_stream(p.data + t0 + off);
+    if (off < len) x[c] = kp_ldg_stream_hint(p.data + t0 + off, policy);
     if (len < G::TB && off + 16 > len) {  // last tile: bytes past the end read as 0
-      uint32_t *xw = reinterpret_cast<uint32_t *>(&x[c]);
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int rem = len - (off + 4 * m);
-        if (rem <= 0) xw[m] = 0u;
-        else if (rem < 4) xw[m] &= (1u << (8 * rem)) - 1u;
-      }
+      x[c].x = fq_keep_bytes(x[c].x, len - off);
+      x[c].y = fq_keep_bytes(x[c].y, len - off - 4);
+      x[c].z = fq_keep_bytes(x[c].z, len - off - 8);
+      x[c].w = fq_keep_bytes(x[c].w, len - off - 12);
     }
   }
 }
@@ -346,7 +374,6 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
   const uint32_t NS = KT == 12 ? 512u : p.n_slices;
   const uint32_t smask = NS - 1u, lomask = (1u << slo) - 1u;
   const uint32_t cap = (uint32_t)FQ_BUCKET_ENTRIES / NS;  // bucket capacity per slice: a multiple of FQ_CHUNK
-  const uint32_t dummy_off = (uint32_t)(offsetof(Smem, dummy) - offsetof(Smem, fill)) + 4u * (uint32_t)lane;
   FqOwner<G> own;
   bool flush_pending = false;
   uint32_t next_tile = 0;                                // thread 0: the tile claimed last
@@ -359,7 +386,9 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
     if (s < NS) { own.qb16[i] = (uint32_t)(__ldg(p.qbase + s) / FQ_CHUNK); own.qcap[i] = __ldg(p.qcap + s); }
   }
   for (int i = tid; i < 48; i += NT) S.raw[FQ_HALO + TB + i] = 0;
-  if (tid < 32) S.dummy[tid] = 0x40000000u;
+  for (uint32_t i = tid; i < sizeof(S.bucket) / 16; i += NT)
+    reinterpret_cast<uint4 *>(S.bucket)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);  // FQ_PAD everywhere
+  for (uint32_t u = 2u + (uint32_t)tid; u <= 64u; u += NT) S.recip[u] = 0xFFFFFFFFu / u + 1u;
   if (tid == 0) {
     S.tileq[0] = atomicAdd(p.counters, 1u);
     S.nbig = 0; S.umax = 0; S.usum = 0;
@@ -369,14 +398,20 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
   __syncthreads();
 
   // one bulk copy per tile: [t0 - 16, t0 + len rounded up to 16); a launch without halo starts a line
+  // the census reads a tile first and wants it to stay in L2 (evict_last); the bulk copy reads it for the last time
+#if FQ_L2HINTS
+  const unsigned long long pol_keep = kp_l2_policy_evict_last(), pol_last_use = kp_l2_policy_evict_first();
+#else
+  const unsigned long long pol_keep = 0, pol_last_use = 0;
+#endif
   auto start_tile_load = [&](uint32_t tile) {
     const uint64_t t0 = (uint64_t)tile * TB;
     const uint32_t len = (uint32_t)((p.n - t0) < (uint64_t)TB ? (p.n - t0) : (uint64_t)TB);
     const uint32_t body = (len + 15u) & ~15u;
     if (t0 > 0 || p.halo_ok) {
-      kp_bulk_load(S.raw, p.data + t0 - FQ_HALO, body + FQ_HALO, &S.mbar);
+      kp_bulk_load(S.raw, p.data + t0 - FQ_HALO, body + FQ_HALO, &S.mbar, pol_last_use);
     } else {
-      kp_bulk_load(S.raw + FQ_HALO, p.data + t0, body, &S.mbar);
+      kp_bulk_load(S.raw + FQ_HALO, p.data + t0, body, &S.mbar, pol_last_use);
     }
   };
 
@@ -387,9 +422,13 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
   {
     const uint32_t tile0 = S.tileq[0];
     uint32_t excl = 0;
+    if (tile0 == 0 && !p.halo_ok && tid < 4) {  // a launch without halo starts a line
+      reinterpret_cast<uint32_t *>(S.raw)[tid] = 0x0A0A0A0Au;
+      kp_fence_proxy_async();  // a later bulk copy writes these bytes again
+    }
     if (tile0 < p.n_tiles) {
       uint4 x[VPT];
-      fq_census_load<G>(p, tile0, tid, x);
+      fq_census_load<G>(p, tile0, tid, pol_keep, x);
       excl = fq_census_masks<G>(x, cur, S.wtot, lane, w);
     }
     if (tid == 0) {
@@ -421,20 +460,22 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
         if (pn) kp_prefetch_l2(p.data + pb, pn);
       }
     }
-    // ---- 1. census of the NEXT tile: the loads overlap the wait for this tile's bytes ------------------------------------
+    // ---- 1. census of the NEXT tile: the loads (L2 hits) overlap the pending copy-out and the wait for this tile's bytes --
     FqCensus<G> nxt;
     nxt.mlo = 0; nxt.mhi = 0; nxt.rank0 = 0;
-    uint32_t nxt_excl = 0;
-    uint4 nx[VPT];
-    if (have_next) fq_census_load<G>(p, tile_next, tid, nx);
-    kp_mbar_wait(&S.mbar, it);
-    if (t0 == 0 && !p.halo_ok && tid < 4) {
-      reinterpret_cast<uint32_t *>(S.raw)[tid] = 0x0A0A0A0Au;
-      kp_fence_proxy_async();  // a later bulk copy writes these bytes again
+    uint32_t nxt_excl = 0, N_next = 0;
+    {
+      uint4 nx[VPT];
+      if (have_next) fq_census_load<G>(p, tile_next, tid, pol_keep, nx);
+      if (flush_pending) {
+        fq_flush_copy<G>(S, p, own, tid, cap, slo, sb, lomask);
+        flush_pending = false;
+      }
+      if (have_next) nxt_excl = fq_census_masks<G>(nx, nxt, wtot_next, lane, w);
     }
-    if (have_next) nxt_excl = fq_census_masks<G>(nx, nxt, wtot_next, lane, w);
+    kp_mbar_wait(&S.mbar, it);
 
-    // ---- 2. warp 0 looks back (every predecessor published a tile ago); the other warps finish the pending copy-out ------
+    // ---- 2. warp 0 looks back (every predecessor published a tile ago) and leaves the tile's framing constants ---------
     if (w == 0) {
       // the line the tile starts in: where did it begin?
       int head = -17;
@@ -442,26 +483,27 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
       const unsigned hm = __ballot_sync(0xffffffffu, head != -17);
       if (hm) head = -(__ffs(hm));
       const unsigned long long g = fq_lookback(p.tile_state, tile, N, g_in, lane);
-      if (lane == 0) { S.G_ = g; S.head = head; }
+      if (lane == 0) {
+        const uint32_t g4 = (uint32_t)g & 3u;
+        const uint32_t jr = (1u - g4) & 3u;                      // first line of the tile (tile relative) on phase 1
+        S.G_ = g;
+        S.ti.head = head;
+        S.ti.jrow0 = jr;
+        S.ti.NRt = N >= jr ? (N - jr) / 4u + 1u : 0u;            // sequence lines that touch the tile
+        // tile lines below jlim are inside max_lines (incomplete last record, -p cap)
+        S.ti.jlim = p.max_lines <= g ? 0u : (p.max_lines - g < 0x7fffffffull ? (uint32_t)(p.max_lines - g) : 0x7fffffffu);
+      }
     }
-    if (flush_pending) {
-      fq_flush_copy<G>(S, p, own, tid, cap, slo, sb, lomask);
-      flush_pending = false;
-    }
-    __syncthreads();  // (2) G, head, wtot_next[]; the buckets may be appended to again
-    uint32_t N_next = 0;
+    __syncthreads();  // (2) the framing constants, wtot_next[]; the buckets may be appended to again
     if (have_next) {
       N_next = fq_census_total<G>(wtot_next, nxt_excl, nxt, lane, w);
       if (tid == 0) fq_lookback_publish(p.tile_state, tile_next, N_next, g_in);
     }
 
-    const unsigned long long Gl = S.G_;
-    const int head = S.head;
-    const uint32_t G4 = (uint32_t)Gl & 3u;
-    const uint32_t jrow0 = (1u - G4) & 3u;                            // first line of the tile (tile relative) on phase 1
-    const uint32_t NRt = N >= jrow0 ? (N - jrow0) / 4u + 1u : 0u;     // sequence lines that touch the tile
-    // tile lines below jlim are inside max_lines (incomplete last record, -p cap)
-    const uint32_t jlim = p.max_lines <= Gl ? 0u : (p.max_lines - Gl < 0x7fffffffull ? (uint32_t)(p.max_lines - Gl) : 0x7fffffffu);
+    const uint4 ti = *reinterpret_cast<const uint4 *>(&S.ti);
+    const int head = (int)ti.x;
+    const uint32_t jrow0 = ti.y, NRt = ti.z, jlim = ti.w;
+    const uint32_t G4 = (1u - jrow0) & 3u;
 
     // ---- 3./4. lines -> rows -> units, in batches of MAXROWS rows -------------------------------------------------------
     for (uint32_t rb = 0; rb == 0 || rb < NRt; rb += G::MAXROWS) {
@@ -472,7 +514,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
         if (rb == 0) {
           // a line that starts exactly with the tile: tag.[0] <> '@' || tmp.[0] <> '+' (Files.ml:213)
           if (head == -1 && len > 0 && (G4 & 1u) == 0u && jlim > 0u) {
-            if (S.raw[FQ_HALO] != (G4 == 0u ? '@' : '+')) atomicMin(p.err_line, Gl);
+            if (S.raw[FQ_HALO] != (G4 == 0u ? '@' : '+')) atomicMin(p.err_line, S.G_);
           }
           if (jrow0 == 0u && NRt) S.rowS[0] = (uint16_t)(head + 1 + FQ_PBIAS);  // the tile starts inside a sequence line
         }
@@ -493,7 +535,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
           if ((ph1 & 1u) == 0u) {
             // header / '+' line: an empty one raises as well (the byte is then '\n')
             if (rb == 0 && j + 1u < jlim && pos + 1 < len) {
-              if (S.raw[FQ_HALO + pos + 1] != (ph1 == 0u ? '@' : '+')) atomicMin(p.err_line, Gl + j + 1ull);
+              if (S.raw[FQ_HALO + pos + 1] != (ph1 == 0u ? '@' : '+')) atomicMin(p.err_line, S.G_ + j + 1ull);
             }
             if (ph1 == 2u) {                                 // line j is a sequence line: it ends here
               const uint32_t r = (j - jrow0) / 4u - rb;
@@ -511,7 +553,9 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
       uint32_t nunits = 0, rinfo = 0;
       if ((uint32_t)tid < nrows && NRt) {
         const int st = (int)S.rowS[tid] - FQ_PBIAS, e = (int)S.rowE[tid] - FQ_PBIAS;
-        const int a = st + k - 1 > 0 ? st + k - 1 : 0;  // first window end: line start + k - 1, inside the tile
+        // first window end: line start + k - 1, inside the tile, rounded down to a word boundary (the windows this
+        // adds hold the line feed before the row: they are not valid)
+        const int a = st + k - 1 > 0 ? (st + k - 1) & ~3 : 0;
         if (jrow0 + 4u * (rb + (uint32_t)tid) < jlim && e > a) {
           nunits = (uint32_t)(e - a + FQ_W - 1) / FQ_W;
           rinfo = (uint32_t)a | ((uint32_t)e << 16);
@@ -527,7 +571,8 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
       const uint32_t NR = NRt ? nrows : 0u;
       const uint32_t UPR = S.umax, usum = S.usum;
       const bool uniform = NR * UPR <= usum + (usum >> 2) + 64u;
-      const uint32_t recip = UPR > 1u ? 0xFFFFFFFFu / UPR + 1u : 0u;  // q / UPR = umulhi(q, recip) for q < 2^16, UPR > 1
+      // q / UPR = umulhi(q, recip) for q < 2^16, UPR > 1
+      const uint32_t recip = UPR <= 1u ? 0u : (UPR <= 64u ? S.recip[UPR] : 0xFFFFFFFFu / UPR + 1u);
       uint32_t U = NR * UPR;
       if (!uniform) {
         const uint32_t ub = fq_block_excl_scan<G::NW>(nunits, S.wtot, U, lane, w);
@@ -554,7 +599,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
       // the state the next launch starts from (only the tile that ends the launch)
       if (tid == 0 && tile == p.n_tiles - 1 && last_batch) {
         KpcStreamCarry co;
-        co.s1.count = Gl + N;
+        co.s1.count = S.G_ + N;
         co.s1.last_hdr = 0;
         int plast = head;  // position of the last line feed of the tile (or of the halo)
         if (N) {
@@ -593,7 +638,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
           if (uniform) {
             const uint32_t r = UPR == 1u ? q : __umulhi(q, recip), u = q - r * UPR;
             const int st = (int)S.rowS[r] - FQ_PBIAS, e = (int)S.rowE[r] - FQ_PBIAS;
-            const int a = (st + k - 1 > 0 ? st + k - 1 : 0) + (int)(u * FQ_W);
+            const int a = (st + k - 1 > 0 ? (st + k - 1) & ~3 : 0) + (int)(u * FQ_W);
             if (jrow0 + 4u * (rb + r) < jlim && a < e) info = (uint32_t)a | ((uint32_t)e << 16);
           } else {
             info = S.uinfo[q];
@@ -602,18 +647,16 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
         if ((info & 0xFFFFu) < (info >> 16)) {
           const int p0 = (int)(info & 0xFFFFu), e = (int)(info >> 16);
           const int nvalid = e - p0 < FQ_W ? e - p0 : FQ_W;
-          // bytes [p0 - 12, p0 + 16): 8 aligned words, funnel-shifted to 7
-          const int A = FQ_HALO + p0 - FQ_CTX;
-          const uint32_t *rw = reinterpret_cast<const uint32_t *>(S.raw) + (A >> 2);
-          const uint32_t sh = (uint32_t)(A & 3) * 8u;
-          uint32_t xw[8];
+          // bytes [p0 - 12, p0 + 16): 7 words (units start on word boundaries)
+          const uint32_t *rw = reinterpret_cast<const uint32_t *>(S.raw) + ((FQ_HALO + p0 - FQ_CTX) >> 2);
+          uint32_t xw[7];
 #pragma unroll
-          for (int m = 0; m < 8; ++m) xw[m] = rw[m];
+          for (int m = 0; m < 7; ++m) xw[m] = rw[m];
           // the 2-bit fields and the 0x80 "not a base" flags of four bytes are gathered with one dot product each
           uint32_t xh = 0, xl = 0, iA = 0, iB = 0, iC = 0, iD = 0;
 #pragma unroll
           for (int m = 0; m < 7; ++m) {
-            const uint32_t wd = __funnelshift_r(xw[m], xw[m + 1], sh);
+            const uint32_t wd = xw[m];
             uint32_t nz;
             const uint32_t x = fq_classify4(wd, nz);
             if (m < 3) xh = __dp4a(x, 0x01041040u, xh << 8); else xl = __dp4a(x, 0x01041040u, xl << 8);
@@ -663,14 +706,17 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
         // when the k-mers are equal
         if (ok) {
           uint32_t pending = ok;
+          if (KT == 12) {
+#pragma unroll
+            for (int jw = 0; jw < FQ_W; jw += FQ_APPEND_GROUP) fq_append4_k12<DS>(S, hi24, lo32, rhi, rlo, jw, ok, pending);
+          }
 #pragma unroll
           for (int jw = 0; jw < FQ_W; ++jw) {
+            if (KT == 12) break;
             uint32_t kk = fq_top_word(hi24, lo32, 34 + 2 * jw - 2 * k);
             if (DS) kk = kp_umin(kk, fq_top_word(rhi, rlo, 38 - 2 * jw));
             const uint32_t bit = 1u << (FQ_W - 1 - jw);
-            if (KT == 12) {
-              fq_append_k12(S, kk, pending, bit, ok, dummy_off);
-            } else if (pending & bit) {
+            if (pending & bit) {
               const uint32_t key = kk >> (32 - 2 * k);
               const uint32_t sl = fq_slice_of(key, slo, smask);
               const uint32_t pos = kp_atoms_add(s_fill + 4u * sl, 1u);

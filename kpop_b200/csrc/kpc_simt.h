@@ -52,6 +52,41 @@ KP_DEV uint4 kp_ldg_stream(const uint8_t *p) {
   return x;
 #endif
 }
+// the same load with an L2 eviction policy (see kp_l2_policy_*)
+KP_DEV uint4 kp_ldg_stream_hint(const uint8_t *p, unsigned long long policy) {
+#ifdef KPC_SIMT_EMUL
+  (void)policy;
+  uint4 x;
+  memcpy(&x, p, 16);
+  return x;
+#else
+  if (!policy) return kp_ldg_stream(p);
+  uint4 x;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+               : "l"(p), "l"(policy));
+  return x;
+#endif
+}
+// L2 eviction policies: a line read with evict_last stays until it is read with evict_first (its last use)
+KP_DEV unsigned long long kp_l2_policy_evict_last() {
+#ifdef KPC_SIMT_EMUL
+  return 1;
+#else
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+#endif
+}
+KP_DEV unsigned long long kp_l2_policy_evict_first() {
+#ifdef KPC_SIMT_EMUL
+  return 2;
+#else
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+#endif
+}
 // pull [p, p + n) into L2 (n a multiple of 16)
 KP_DEV void kp_prefetch_l2(const uint8_t *p, uint32_t n) {
 #ifdef KPC_SIMT_EMUL
@@ -101,15 +136,20 @@ KP_DEV void kp_mbar_init(unsigned long long *bar, uint32_t count) {
 #endif
 }
 // one thread: announce `bytes` and start the copy; dst, src and bytes are multiples of 16
-KP_DEV void kp_bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+KP_DEV void kp_bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar, unsigned long long policy) {
 #ifdef KPC_SIMT_EMUL
+  (void)policy;
   memcpy(dst, src, bytes);
   *bar += 1;  // completed phases
 #else
   const uint32_t b = kp_smem_addr(bar), d = kp_smem_addr(dst);
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+  if (policy)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(b), "l"(policy) : "memory");
+  else
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
 #endif
 }
 // all threads: wait until phase number `phase` (0, 1, 2, ...) of the barrier has completed
