@@ -77,3 +77,21 @@ print("ok")
 ''' % (ROOT, os.path.join(EMUL_DIR, "_build", "libkpopcount_emul.so"), label)
     p = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert p.returncode == 0 and p.stdout.strip() == b"ok", p.stderr.decode(errors="replace")
+
+
+def test_emul_cli_output_prefix_and_pipes(emul_bin, oracle_bin, tmp_path):
+    """-o <prefix> / -o /dev/stdout (lib/KMerDB.ml:26-31) and `cat x.fa | KPopCount ... -f /dev/stdin` (README.md:89-96) through
+    the same kpopcount_main.cpp the GPU binary is built from."""
+    fa = tmp_path / "a.fa"
+    fa.write_bytes(b">s one\nACGTNACGTTGACCA\nGGTAC\n>t\nacgtacgtacgt\n")
+    env = emul_env("8x4", "64")
+    rc, out, err = run_cli(emul_bin, ["-k", "3", "-l", "x", "-f", str(fa), "-o", str(tmp_path / "pre")], env=env)
+    rc_o, out_o, _ = run_cli(oracle_bin, ["-k", "3", "-l", "x", "-f", str(fa)])
+    assert rc == 0 and out == b"", err
+    assert (tmp_path / "pre.KPopSpectra.txt").read_bytes() == out_o
+    rc, out, err = run_cli(emul_bin, ["-k", "3", "-l", "x", "-f", str(fa), "-o", "/dev/stdout"], env=env)
+    assert (rc, out) == (0, out_o), err
+    for argv in (["-k", "5", "-L"], ["-k", "4", "-l", "w"], ["-k", "13", "-l", "w"]):
+        rc_o, out_o, _ = run_cli(oracle_bin, argv + ["-f", str(fa)])
+        rc_e, out_e, err_e = run_cli(emul_bin, argv + ["-f", "/dev/stdin"], stdin=fa.read_bytes(), env=env)
+        assert (rc_e, out_e) == (rc_o, out_o), err_e

@@ -81,16 +81,21 @@ def test_gpu_reference_fixtures(gpu_bin, oracle_bin, fixture_dir, chunk):
 @pytest.mark.parametrize("seed", range(6))
 def test_gpu_fuzz_vs_oracle(gpu_bin, oracle_bin, tmp_path, seed):
     rng = random.Random(5000 + seed)
+    refused = []
     for idx in range(25):
         argv, fmt = one_case(rng, tmp_path, idx)
         chunk = rng.choice([None, 4096, 70_000])
         rc_o, out_o, err_o = run_cli(oracle_bin, argv)
         rc_g, out_g, err_g = run_cli(gpu_bin, argv, env=env_chunk(chunk))
-        if rc_g == 2 and b"code -9" in err_g:
+        if rc_g == 2 and b"code -9" in err_g:  # KPC_E_UNSUPPORTED: an explicit refusal (DESIGN.md lists the shapes)
+            refused.append((idx, err_g.decode(errors="replace").strip()[-160:]))
             continue
         ctx = f"seed={seed} case={idx} chunk={chunk} argv={' '.join(argv)}\n{err_g.decode(errors='replace')}"
         assert rc_g == rc_o, ctx
         assert out_g == out_o, ctx
+    # refusals are counted, not hidden; the two shapes that remain are listed in DESIGN.md (section 8)
+    assert len(refused) <= 3, refused
+    assert all("staging size" in m or "paired-end input whose table reaches -M" in m for _, m in refused), refused
 
 
 def test_gpu_longer_inputs_every_mode(gpu_bin, oracle_bin, tmp_path):
@@ -243,3 +248,39 @@ def test_gpu_full_size_properties():
         want = np.zeros(4 ** 12, dtype=np.uint32)
         lib.fd_count_fastq_dense(host, len(host), 12, want.ctypes.data_as(ctypes.c_void_p), 16)
         assert np.array_equal(table_of(0, pre), want.astype(np.uint64))
+
+
+# ---- the command line as the pipelines of the reference use it (README.md:89-96: everything is a pipe) -------------------
+def test_gpu_cli_output_prefix_and_dev_stdout(gpu_bin, tmp_path):
+    """-o <prefix> writes <prefix>.KPopSpectra.txt, a /dev/* name is taken verbatim (lib/KMerDB.ml:26-31)."""
+    fa = tmp_path / "a.fa"
+    fa.write_bytes(b">s\nACGTNACG\n")
+    rc, out, err = run_cli(gpu_bin, ["-k", "3", "-l", "x", "-f", str(fa), "-o", str(tmp_path / "pre")])
+    assert rc == 0 and out == b"", err
+    assert (tmp_path / "pre.KPopSpectra.txt").read_bytes() == b"\tx\n06\t3\n"
+    rc, out, err = run_cli(gpu_bin, ["-k", "3", "-l", "x", "-f", str(fa), "-o", "/dev/stdout"])
+    assert rc == 0 and out == b"\tx\n06\t3\n", err
+
+
+def test_gpu_cli_reads_pipes(gpu_bin, oracle_bin, fixture_dir, tmp_path):
+    """`cat x.fa | KPopCount -k 5 -L -f /dev/stdin` (the quick-start pipeline), and paired-end input from two FIFOs."""
+    fa = os.path.join(fixture_dir, "wuhan.fasta")
+    data = open(fa, "rb").read()
+    for argv in (["-k", "5", "-L"], ["-k", "12", "-l", "w"], ["-k", "21", "-l", "w"]):
+        rc_o, out_o, _ = run_cli(oracle_bin, argv + ["-f", fa])
+        rc_g, out_g, err_g = run_cli(gpu_bin, argv + ["-f", "/dev/stdin"], stdin=data)
+        assert (rc_g, out_g) == (rc_o, out_o), err_g.decode(errors="replace")[-300:]
+    rng = random.Random(4)
+    m1 = b"".join(b"@a%d/1\n%s\n+\n%s\n" % (i, bytes(rng.choices(b"ACGT", k=80)), b"I" * 80) for i in range(500))
+    m2 = b"".join(b"@a%d/2\n%s\n+\n%s\n" % (i, bytes(rng.choices(b"ACGT", k=60)), b"I" * 60) for i in range(500))
+    f1, f2 = tmp_path / "m1.fq", tmp_path / "m2.fq"
+    f1.write_bytes(m1); f2.write_bytes(m2)
+    p1, p2 = str(tmp_path / "p1"), str(tmp_path / "p2")
+    os.mkfifo(p1); os.mkfifo(p2)
+    for argv in (["-k", "12", "-l", "x"], ["-k", "7", "-L"]):
+        rc_o, out_o, _ = run_cli(oracle_bin, argv + ["-p", str(f1), str(f2)])
+        writers = [subprocess.Popen(["sh", "-c", f"cat {f1} > {p1}"]), subprocess.Popen(["sh", "-c", f"cat {f2} > {p2}"])]
+        rc_g, out_g, err_g = run_cli(gpu_bin, argv + ["-p", p1, p2])
+        for w in writers:
+            w.wait()
+        assert (rc_g, out_g) == (rc_o, out_o), err_g.decode(errors="replace")[-300:]
