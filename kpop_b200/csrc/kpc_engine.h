@@ -106,7 +106,8 @@ class KpcEngine {
   // --- kernels ---
   void launch_tiles(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch, uint64_t max_lines,
                     int sink_kind, const KpcHashSink *hs, const KpcTupleSink *ts, bool with_recs,
-                    unsigned long long *probe_pos, uint64_t probe_from);
+                    unsigned long long *probe_pos, uint64_t probe_from, const KpcBucketCountSink *bc = nullptr,
+                    const KpcBucketScatterSink *bs = nullptr);
   void advance(StreamState &st, size_t len);
   void ensure_desc(uint64_t n_tiles);
 
@@ -118,6 +119,9 @@ class KpcEngine {
   void hash_ensure_capacity(uint64_t need);
   void hash_dump(bool clear);
   void hash_finish();
+  bool sort_usable(const StreamState &st, size_t len, bool final_launch) const;
+  bool sort_process(StreamState &st, int mate, const uint8_t *dev, size_t len, uint64_t max_lines);
+  void sort_migrate();
   void tuple_process(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch, uint64_t max_lines);
   void tuple_flush(bool input_done);
   void tuple_finish();
@@ -194,6 +198,14 @@ class KpcEngine {
   unsigned long long *d_hstat_ = nullptr;  // [0] distinct, [1] overflow
   uint64_t hdistinct_ = 0;
   uint64_t epoch_rank_lo_ = 0;  // windows with rank < this belong to already dumped epochs
+  // sort path: a whole sample counted without the hash table (kpc_bucketsort.cuh); its entries wait here for finish()
+  bool sort_enabled_ = true;
+  bool sorted_pending_ = false;
+  uint64_t sorted_slots_ = 0;     // entry slots (windows of the sample); slots with count 0 print nothing
+  uint64_t sorted_distinct_ = 0;
+  void *sort_buf_ = nullptr;
+  size_t sort_buf_cap_ = 0;
+  unsigned long long *skeys_ = nullptr, *scounts_ = nullptr, *sranks_ = nullptr;
 
   // tuple (-L)
   unsigned long long *tkeys_ = nullptr, *tranks_ = nullptr;

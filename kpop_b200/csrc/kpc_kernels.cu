@@ -14,6 +14,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "kpc_kernels.h"
+#include "kpc_bucketsort.cuh"
 #include "kpc_synth.h"
 #include "../../include/kpopcount.h"
 
@@ -86,6 +87,8 @@ static void launch_tiles_s(const KpcTileLaunch &L, rt_stream s) {
     case KPC_SINK_DENSE: launch_tiles_t<FMT, CONTENT>(L.p, L.dense, s); break;
     case KPC_SINK_HASH: launch_tiles_t<FMT, CONTENT>(L.p, L.hash, s); break;
     case KPC_SINK_TUPLE: launch_tiles_t<FMT, CONTENT>(L.p, L.tuple, s); break;
+    case KPC_SINK_BCOUNT: launch_tiles_t<FMT, CONTENT>(L.p, L.bcount, s); break;
+    case KPC_SINK_BSCATTER: launch_tiles_t<FMT, CONTENT>(L.p, L.bscatter, s); break;
     default: launch_tiles_t<FMT, CONTENT>(L.p, KpcNullSink(), s); break;
   }
 }
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     off += l[j];
   }
 }
-size_t kpc_k_scan_scratch_bytes(uint64_t n) { return ((n + SCAN_BLK - 1) / SCAN_BLK + 2) * sizeof(unsigned long long); }
+size_t kpc_k_scan_scratch_bytes(uint64_t n) { return ((n + SCAN_BLK - 1) / SCAN_BLK + 2) * sizeof(unsigned long long) + 512; }
 
 // total (number of output units) lands in *total_out
 template <class LenF, class WriteF>
@@ -319,7 +322,10 @@ __device__ __forceinline__ int dec_digits(unsigned long long v) {
 struct FormatLen {
   const unsigned long long *counts;
   int w;
-  __device__ unsigned long long operator()(uint64_t i) const { return (unsigned long long)(w + 2 + dec_digits(counts[i])); }
+  __device__ unsigned long long operator()(uint64_t i) const {  // an entry with count 0 (sort path filler) prints nothing
+    const unsigned long long c = counts[i];
+    return c ? (unsigned long long)(w + 2 + dec_digits(c)) : 0ull;
+  }
 };
 __global__ void __launch_bounds__(SCAN_THREADS)
     format_scatter_kernel(const unsigned long long *keys, const unsigned long long *counts, int w, char *out, uint64_t n,
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 #pragma unroll
   for (int j = 0; j < SCAN_ITEMS; ++j) {
     c[j] = (i0 + j < n) ? counts[i0 + j] : 0ull;
-    l[j] = (i0 + j < n) ? (uint32_t)(w + 2 + dec_digits(c[j])) : 0u;
+    l[j] = (i0 + j < n && c[j]) ? (uint32_t)(w + 2 + dec_digits(c[j])) : 0u;
     s += l[j];
   }
   unsigned long long tot;
@@ -342,7 +348,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   char *st = fmt_stage + skew;
 #pragma unroll
   for (int j = 0; j < SCAN_ITEMS; ++j) {
-    if (i0 + j < n) {
+    if (l[j]) {
       char *o = st + off;
       unsigned long long key = keys[i0 + j];
       for (int q = w - 1; q >= 0; --q) { o[q] = "0123456789abcdef"[key & 15ull]; key >>= 4; }
@@ -436,6 +442,47 @@ void kpc_k_hash_extract(const unsigned long long *keys, const unsigned long long
                         unsigned long long *ocounts, unsigned long long *oranks, unsigned long long *n_out,
                         void *scratch, rt_stream s) {
   run_scan(HashLen{keys, counts}, HashWrite{keys, counts, ranks, okeys, ocounts, oranks}, cap, n_out, scratch, s);
+}
+
+// =================================================================================================
+// sort path: bucket offsets + per-bucket finalize (kpc_bucketsort.cuh)
+// =================================================================================================
+struct BucketLen {
+  const uint32_t *hist;
+  __device__ unsigned long long operator()(uint64_t i) const { return hist[i]; }
+};
+struct BucketWrite {
+  uint32_t *offsets;
+  __device__ void operator()(uint64_t i, unsigned long long off, unsigned long long) const { offsets[i] = (uint32_t)off; }
+};
+__global__ void bucket_total_kernel(const unsigned long long *total, uint32_t *offsets, uint32_t nb) {
+  offsets[nb] = (uint32_t)*total;
+}
+void kpc_k_bucket_offsets(const uint32_t *hist, uint32_t nb, uint32_t *offsets, void *scratch, rt_stream s) {
+  unsigned long long *total = (unsigned long long *)scratch;
+  run_scan(BucketLen{hist}, BucketWrite{offsets}, nb, total, (char *)scratch + 256, s);
+  bucket_total_kernel<<<1, 1, 0, cs(s)>>>(total, offsets, nb);
+  CUDA_CHECK(cudaGetLastError());
+}
+extern __shared__ __align__(16) uint8_t kpc_dyn_smem[];
+__global__ void __launch_bounds__(256) bucket_finalize_small_kernel(const KpcBucketFinalize F) {
+  kpc_bucket_finalize_small_body<256>(F);
+}
+__global__ void __launch_bounds__(256) bucket_finalize_heavy_kernel(const KpcBucketFinalize F) {
+  kpc_bucket_finalize_heavy_body<256>(F, kpc_dyn_smem);
+}
+void kpc_k_bucket_finalize(const KpcBucketFinalize &F, rt_stream s) {
+  static bool attr = false;
+  if (!attr) {
+    CUDA_CHECK(cudaFuncSetAttribute(bucket_finalize_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(KpcBsHeavySmem)));
+    attr = true;
+  }
+  bucket_finalize_small_kernel<<<ew_grid(F.nb), 256, 0, cs(s)>>>(F);
+  CUDA_CHECK(cudaGetLastError());
+  // the heavy groups (usually none): a fixed grid walks the list the first kernel left
+  bucket_finalize_heavy_kernel<<<148, 256, sizeof(KpcBsHeavySmem), cs(s)>>>(F);
+  CUDA_CHECK(cudaGetLastError());
 }
 
 // =================================================================================================

@@ -4,7 +4,7 @@
 #include "kpc_rt.h"
 #include "kpc_tile.cuh"
 
-enum { KPC_SINK_NULL = 0, KPC_SINK_DENSE = 1, KPC_SINK_HASH = 2, KPC_SINK_TUPLE = 3 };
+enum { KPC_SINK_NULL = 0, KPC_SINK_DENSE = 1, KPC_SINK_HASH = 2, KPC_SINK_TUPLE = 3, KPC_SINK_BCOUNT = 4, KPC_SINK_BSCATTER = 5 };
 
 struct KpcTileLaunch {
   int fmt, content, sink;
@@ -12,6 +12,8 @@ struct KpcTileLaunch {
   KpcDenseSink dense;
   KpcHashSink hash;
   KpcTupleSink tuple;
+  KpcBucketCountSink bcount;
+  KpcBucketScatterSink bscatter;
 };
 
 // bytes per tile of the framing kernel (the engine sizes the descriptor array with it)
@@ -52,6 +54,25 @@ void kpc_k_hash_extract(const unsigned long long *keys, const unsigned long long
                         const unsigned long long *ranks, uint64_t cap, unsigned long long *okeys,
                         unsigned long long *ocounts, unsigned long long *oranks, unsigned long long *n_out,
                         void *scratch, rt_stream s);
+
+// ---- sort path (kpc_bucketsort.cuh): a whole large-k sample without a hash table ----
+// exclusive prefix sums of hist[0..nb) into offsets[0..nb]; offsets[nb] = total
+void kpc_k_bucket_offsets(const uint32_t *hist, uint32_t nb, uint32_t *offsets, void *scratch, rt_stream s);
+struct KpcBucketFinalize {
+  const uint32_t *offsets;            // nb + 1 entries
+  uint32_t nb;
+  unsigned long long *keys, *ranks;   // in: pairs grouped by coarse bucket; out: entries
+  unsigned long long *counts;         // out
+  unsigned long long bmask;           // B - 1
+  uint32_t *heavy_list;               // groups left to the CTA-wide kernel
+  uint32_t heavy_cap;
+  unsigned long long *stats;          // [0] distinct keys, [1] too-heavy flag, [2] number of heavy groups
+};
+
+// every bucket range of (keys, ranks): duplicates merged (counts = multiplicity, ranks = first occurrence), entries
+// left in Hashtbl.iter order, the slots duplicates leave behind get key ~0 / count 0.  stats[0] += distinct keys,
+// stats[1] != 0 when a range is too large for this path (the caller then falls back to the hash table).
+void kpc_k_bucket_finalize(const KpcBucketFinalize &F, rt_stream s);
 
 // ---- ordering ----
 // OCaml Hashtbl.iter order: ascending (key mod B), newest (largest rank) first inside a

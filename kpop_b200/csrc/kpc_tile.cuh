@@ -243,6 +243,31 @@ struct KpcTupleSink {
   }
 };
 
+// Sort path (a whole sample in one launch, large k: DESIGN.md section 6): two passes over the input instead of a hash
+// table.  Pass 1 counts the windows of every coarse bucket -- the top bits of (key mod B), B = OCaml's bucket count --,
+// pass 2 drops every window into its bucket's range of one (key, rank) array (the order inside a range is arbitrary:
+// kpc_bucketsort.cuh sorts, merges duplicates and restores Hashtbl.iter order range by range).
+struct KpcBucketCountSink {
+  uint32_t *hist;
+  uint64_t bmask;  // B - 1
+  int cshift;      // coarse bucket = (key & bmask) >> cshift
+  KPC_HD void emit(uint64_t key, uint64_t /*rank*/, uint64_t /*rec*/) const { kpc_red_add_u32(hist + ((key & bmask) >> cshift), 1u); }
+};
+struct KpcBucketScatterSink {
+  uint32_t *remaining;       // pass 1's counts, counted down to zero here
+  const uint32_t *offsets;   // exclusive prefix sums of the counts
+  unsigned long long *keys, *ranks;
+  uint64_t bmask;
+  int cshift;
+  KPC_HD void emit(uint64_t key, uint64_t rank, uint64_t /*rec*/) const {
+    const uint64_t b = (key & bmask) >> cshift;
+    const uint32_t left = kpc_atomic_add_u32(remaining + b, 0xFFFFFFFFu);  // -1
+    const uint64_t pos = (uint64_t)offsets[b] + left - 1u;
+    keys[pos] = key;
+    ranks[pos] = rank;
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // shared memory of one CTA
 // ------------------------------------------------------------------------------------------------

@@ -49,6 +49,8 @@ void run_s(const KpcTileLaunch &L) {
     case KPC_SINK_DENSE: run_tiles<NT, SEG, FMT, CONTENT>(L.p, L.dense); break;
     case KPC_SINK_HASH: run_tiles<NT, SEG, FMT, CONTENT>(L.p, L.hash); break;
     case KPC_SINK_TUPLE: run_tiles<NT, SEG, FMT, CONTENT>(L.p, L.tuple); break;
+    case KPC_SINK_BCOUNT: run_tiles<NT, SEG, FMT, CONTENT>(L.p, L.bcount); break;
+    case KPC_SINK_BSCATTER: run_tiles<NT, SEG, FMT, CONTENT>(L.p, L.bscatter); break;
     default: run_tiles<NT, SEG, FMT, CONTENT>(L.p, KpcNullSink()); break;
   }
 }
@@ -114,8 +116,13 @@ void kpc_k_format(const unsigned long long *keys, const unsigned long long *coun
                   char *out, unsigned long long *out_len, void *, rt_stream) {
   size_t o = 0;
   for (uint64_t i = 0; i < n; ++i)
-    o += (size_t)sprintf(out + o, "%0*llx\t%llu\n", hex_width, keys[i], counts[i]);
+    if (counts[i]) o += (size_t)sprintf(out + o, "%0*llx\t%llu\n", hex_width, keys[i], counts[i]);
   *out_len = o;
+}
+void kpc_k_bucket_offsets(const uint32_t *hist, uint32_t nb, uint32_t *offsets, void *, rt_stream) {
+  uint32_t acc = 0;
+  for (uint32_t i = 0; i < nb; ++i) { offsets[i] = acc; acc += hist[i]; }
+  offsets[nb] = acc;
 }
 void kpc_k_hash_clear(unsigned long long *keys, unsigned long long *counts, unsigned long long *ranks, uint64_t cap, rt_stream) {
   for (uint64_t i = 0; i < cap; ++i) { keys[i] = ~0ull; counts[i] = 0; ranks[i] = ~0ull; }
