@@ -34,6 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 C3_RECORDS = 31_781_305          # first whole records <= 10^10 bytes
+C5_RECORDS = 316_807_313         # first whole records <= 10^11 bytes
 SEED = 3
 K = 12
 ORACLE = os.path.join(ROOT, "oracle", "_build", "kpopcount_oracle")
@@ -47,7 +48,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--records-per-gpu", type=int, default=C3_RECORDS)
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"],
+                    help="c3: 10 GB of reads per GPU, k = 12 (the headline, weak scaling); c5: ONE 100 GB stream split across the "
+                         "GPUs (strong scaling); c4: ~5 Mb genomes at k = 30, sharded by sample")
+    ap.add_argument("--records-per-gpu", type=int, default=None)
+    ap.add_argument("--genomes-per-gpu", type=int, default=16)
     ap.add_argument("--cpu-sample-records", type=int, default=1_500_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -181,6 +186,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = max(args.gpus, world)
 
+    if args.workload == "c4":
+        import bench_c4
+        return bench_c4.main(args, rank, world, local_rank, n_gpus)
     if args.impl == "reference":
         return reference_arm(args, rank, world, n_gpus)
 
@@ -192,13 +200,23 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    R = args.records_per_gpu
-    first = rank * R
-    kc = KMerCounter(k=K, label="S3", device=local_rank)
+    # c3: every rank counts its own 10 GB of the seed-3 stream (weak); c5: ONE seed-5 stream of 100 GB cut into `world`
+    # contiguous record ranges (strong: read-chunk sharding)
+    c5 = args.workload == "c5"
+    seed = 5 if c5 else SEED
+    if c5:
+        total = args.records_per_gpu * world if args.records_per_gpu else C5_RECORDS
+        first = rank * total // world
+        R = (rank + 1) * total // world - first
+    else:
+        R = args.records_per_gpu or C3_RECORDS
+        first = rank * R
+    label = "S5" if c5 else "S3"
+    kc = KMerCounter(k=K, label=label, device=local_rank)
     nbytes = kc.synth_offset(first + R) - kc.synth_offset(first)
     data = torch.empty(nbytes + 256, dtype=torch.uint8, device="cuda")
     assert data.data_ptr() % 16 == 0
-    kc.synth_fastq(data.data_ptr(), first, R, SEED)
+    kc.synth_fastq(data.data_ptr(), first, R, seed)
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(kc.stream_handle())
     lo_ptr, _hi, nbins = kc.dense_table()
@@ -380,9 +398,13 @@ def main():
         out = {
             "metric": "k-mers counted/sec (bit-exact) at k=12", "value": total_kmers / (ms_step * 1e-3),
             "unit": "k-mers/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if c5 else "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "%s: synthetic 150bp SE FASTQ, seed 3, %d reads (%d B) per GPU, KPopCount -k 12 -l S3 -s, "
+            "config": {"workload": ("C5: ONE synthetic 150bp SE FASTQ stream, seed 5, %d reads cut into %d contiguous record ranges "
+                                    "(%d reads, %d B on rank 0), KPopCount -k 12 -l S5 -s, dense 4^12 table%s"
+                                    % (R * world if args.records_per_gpu else C5_RECORDS, world, R, nbytes,
+                                       ", NCCL all-reduce of the tables" if world > 1 else "")) if c5 else
+                                   "%s: synthetic 150bp SE FASTQ, seed 3, %d reads (%d B) per GPU, KPopCount -k 12 -l S3 -s, "
                                    "dense 4^12 table%s" % ("C3" if R == C3_RECORDS else "C3 shape, other size", R, nbytes,
                                                            ", NCCL all-reduce of the tables" if world > 1 else ""),
                        "k": K, "records_per_gpu": R, "bytes_per_gpu": int(nbytes), "kmers_total": int(total_kmers),

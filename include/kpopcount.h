@@ -81,7 +81,8 @@ int kpc_begin(kpc_ctx *ctx, int format);
 /* raw file bytes of mate 0 (or 1 for the second file of -p); eof != 0 with the last call for that mate.
  * bytes may point into a kpc_staging buffer (asynchronous) or anywhere else (consumed before returning). */
 int kpc_feed(kpc_ctx *ctx, int mate, const void *bytes, size_t n, int eof);
-/* same, for bytes that already live in device memory (16-byte aligned); used by benchmarks */
+/* same, for bytes that already live in device memory (16-byte aligned); used by benchmarks.  The whole input in one call
+ * (eof != 0).  Dense-table runs take any size; hash-table runs (large k) take inputs up to the staging size (64 MiB). */
 int kpc_feed_device(kpc_ctx *ctx, int mate, const void *device_bytes, size_t n, int eof);
 /* FASTQ.iter_pe stops at the shorter file (Files.ml:228-247): after KPC_E_PE_MISMATCH, create a fresh context,
  * set the limit to the reported number of complete pairs and feed again */
@@ -104,8 +105,19 @@ int kpc_dense_max(kpc_ctx *ctx, unsigned long long *max_count);
 /* otherwise: hi += lo, lo = 0 on every rank, reduce hi (u64) instead */
 int kpc_dense_promote(kpc_ctx *ctx);
 
+/* number of line feeds in n bytes of DEVICE memory (16-byte aligned).  Read-chunk sharding of one FASTQ file needs the
+ * line index every shard starts at (records are four lines and cannot be recognised locally: Files.ml:201-221); the
+ * shards' counts are the only data exchanged.  Synchronous. */
+int kpc_count_newlines(kpc_ctx *ctx, const void *device_bytes, size_t n, unsigned long long *count);
+/* 1 when some bin has been folded into the 64-bit side table (a reduction across ranks must then use kpc_dense_promote) */
+int kpc_dense_has_hi(kpc_ctx *ctx, int *has_hi);
+
 /* empty the tables and forget every input, keeping all allocations (a context can then be used for another run) */
 int kpc_reset(kpc_ctx *ctx);
+/* the same, and the next run gets this spectrum label (bin/KPopCount.ml:158-172).  Batch use: one context serves many
+ * samples, one KMerCounter.compute each -- what a `Parallel ... KPopCount -l <sample>` loop (README.md:579,1020) does with
+ * one process per sample.  The label must stay non-empty (-l) or stay empty (-L): the table kind is fixed at creation. */
+int kpc_reset_label(kpc_ctx *ctx, const char *label);
 /* benchmarking with device-resident input: format the dump on the device but leave the text in HBM */
 int kpc_discard_text(kpc_ctx *ctx, int discard);
 unsigned long long kpc_text_bytes(const kpc_ctx *ctx); /* bytes of spectra text produced since create / reset */

@@ -24,6 +24,9 @@ PROTOTYPES = {
     "kpc_staging": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]),
     "kpc_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "kpc_feed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
+    "kpc_count_newlines": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_ulonglong)]),
+    "kpc_dense_has_hi": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
+    "kpc_reset_label": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
     "kpc_feed_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
     "kpc_set_pair_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong]),
     "kpc_complete_pairs": (ctypes.c_longlong, [ctypes.c_void_p]),

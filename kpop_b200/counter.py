@@ -126,6 +126,12 @@ class KMerCounter:
         self._check(self._lib.kpc_reset(self._ctx))
         self._chunks = []
 
+    def reset_label(self, label):
+        """Empty the tables and give the next run this label: one context serves many samples (batch use)."""
+        self._check(self._lib.kpc_reset_label(self._ctx, label.encode()))
+        self.label = label
+        self._chunks = []
+
     def discard_text(self, flag=True):
         self._check(self._lib.kpc_discard_text(self._ctx, 1 if flag else 0))
 
@@ -174,6 +180,17 @@ class KMerCounter:
         out = ctypes.c_ulonglong()
         self._check(self._lib.kpc_dense_max(self._ctx, ctypes.byref(out)))
         return out.value
+
+    def dense_has_hi(self):
+        v = ctypes.c_int(0)
+        self._check(self._lib.kpc_dense_has_hi(self._ctx, ctypes.byref(v)))
+        return bool(v.value)
+
+    def count_newlines(self, device_ptr, n):
+        """Line feeds in n bytes of device memory (16-byte aligned pointer)."""
+        v = ctypes.c_ulonglong(0)
+        self._check(self._lib.kpc_count_newlines(self._ctx, ctypes.c_void_p(device_ptr), n, ctypes.byref(v)))
+        return int(v.value)
 
     def dense_promote(self):
         self._check(self._lib.kpc_dense_promote(self._ctx))

@@ -97,6 +97,10 @@ unsigned long long kpc_text_bytes(const kpc_ctx *ctx) { return (ctx && ctx->engi
 int kpc_reset(kpc_ctx *ctx) {
   return guarded(ctx, [&](KpcEngine &e) { e.reset(); });
 }
+int kpc_reset_label(kpc_ctx *ctx, const char *label) {
+  if (!label) return KPC_E_ARG;
+  return guarded(ctx, [&](KpcEngine &e) { e.reset_label(label); });
+}
 int kpc_staging_slots(const kpc_ctx *ctx) { return (ctx && ctx->engine) ? ctx->engine->staging_slots() : 0; }
 void *kpc_staging(kpc_ctx *ctx, int slot, size_t *capacity) {
   void *p = nullptr;
@@ -135,6 +139,14 @@ int kpc_dense_table(kpc_ctx *ctx, void **lo_u32, void **hi_u64, unsigned long lo
 int kpc_dense_max(kpc_ctx *ctx, unsigned long long *max_count) {
   if (!max_count) return KPC_E_ARG;
   return guarded(ctx, [&](KpcEngine &e) { *max_count = e.dense_max(); });
+}
+int kpc_count_newlines(kpc_ctx *ctx, const void *device_bytes, size_t n, unsigned long long *count) {
+  if (!count || (n && !device_bytes)) return KPC_E_ARG;
+  return guarded(ctx, [&](KpcEngine &e) { *count = e.count_newlines_device((const uint8_t *)device_bytes, n); });
+}
+int kpc_dense_has_hi(kpc_ctx *ctx, int *has_hi) {
+  if (!has_hi) return KPC_E_ARG;
+  return guarded(ctx, [&](KpcEngine &e) { *has_hi = e.dense_has_hi() ? 1 : 0; });
 }
 int kpc_dense_promote(kpc_ctx *ctx) {
   return guarded(ctx, [&](KpcEngine &e) { e.dense_promote(); });

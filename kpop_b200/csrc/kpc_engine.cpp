@@ -295,6 +295,15 @@ void KpcEngine::reset() {
   }
 }
 
+void KpcEngine::reset_label(const std::string &label) {
+  std::string clean;
+  if (!strip_quotes(label, clean)) throw KpcError(KPC_E_QUOTES_IN_NAME, "Spectrum labels must not contain quotes");
+  if (clean.empty() != cfg_.label.empty())
+    throw KpcError(KPC_E_ARG, "kpc_reset_label cannot switch between -l and -L (the table kind is fixed at creation)");
+  reset();
+  cfg_.label = clean;
+}
+
 void KpcEngine::begin(int format) {
   if (failed_) throw KpcError(KPC_E_STATE, "context is in a failed state");
   if (in_input_) throw KpcError(KPC_E_STATE, "kpc_begin while another input is open");
@@ -470,12 +479,36 @@ void KpcEngine::submit_host(StreamState &st, int mate, const Piece *pc, int npc,
 void KpcEngine::feed_device(int mate, const uint8_t *dev, size_t n, bool eof) {
   if (failed_) throw KpcError(KPC_E_STATE, "context is in a failed state");
   if (!in_input_) throw KpcError(KPC_E_STATE, "kpc_feed_device outside kpc_begin / kpc_end");
-  if (mode_ != DENSE) throw KpcError(KPC_E_UNSUPPORTED, "kpc_feed_device is only available on the dense-table path");
   if (!eof) throw KpcError(KPC_E_UNSUPPORTED, "kpc_feed_device takes a whole input in one call (eof must be set)");
   if (mate < 0 || mate > 1 || (mate == 1 && format_ != KPC_FASTQ_PE)) throw KpcError(KPC_E_ARG, "bad mate index");
   if (((uintptr_t)dev & 15) != 0) throw KpcError(KPC_E_ARG, "device input must be 16-byte aligned");
   StreamState &st = streams_[mate];
   if (st.eof || st.fed || st.hold_len) throw KpcError(KPC_E_UNSUPPORTED, "kpc_feed_device cannot be mixed with kpc_feed");
+  if (mode_ != DENSE) {
+    // hash-table / -L runs: one launch, through a ring buffer (room for the line feed a last unterminated line gets)
+    if (mode_ == TUPLE) throw KpcError(KPC_E_UNSUPPORTED, "kpc_feed_device is not available with -L (record names are cut on the host)");
+    if (n > chunk_cap_) throw KpcError(KPC_E_UNSUPPORTED, "device inputs on the hash-table path are limited to the staging size");
+    st.eof = true;
+    RingSlot &slot = next_slot();
+    if (slot.used) rt_stream_wait(compute_, slot.computed);
+    size_t tl = n;
+    if (n) {
+      st.any = true;
+      rt_d2d(slot.buf, dev, n, compute_);
+      rt_d2h(h_tmp_ + 24, dev + (n - 1), 1, compute_);
+      rt_stream_sync(compute_);
+      st.last_byte = *(const uint8_t *)(h_tmp_ + 24);
+      if (st.last_byte != '\n') {
+        *(uint8_t *)(h_tmp_ + 24) = '\n';
+        rt_h2d(slot.buf + tl, h_tmp_ + 24, 1, compute_);
+        tl += 1;
+      }
+    }
+    run_launch(st, mate, slot.buf, tl, true, false);
+    rt_event_record(slot.computed, compute_);
+    slot.used = true;
+    return;
+  }
   st.eof = true;
   if (!n) { run_launch(st, mate, dev, 0, true, false); return; }
   st.any = true;
@@ -826,6 +859,15 @@ unsigned long long KpcEngine::dense_max() {
   rt_stream_sync(compute_);
   return h_tmp_[5];
 }
+unsigned long long KpcEngine::count_newlines_device(const uint8_t *dev, size_t n) {
+  if (((uintptr_t)dev & 15) != 0) throw KpcError(KPC_E_ARG, "device input must be 16-byte aligned");
+  rt_memset(d_tmp_ + 9, 0, 8, compute_);
+  kpc_k_count_newlines(dev, n, d_tmp_ + 9, compute_);
+  launches_ += n ? 1 : 0;
+  rt_d2h(h_tmp_ + 9, d_tmp_ + 9, 8, compute_);
+  rt_stream_sync(compute_);
+  return h_tmp_[9];
+}
 void KpcEngine::dense_promote() {
   if (mode_ != DENSE) throw KpcError(KPC_E_STATE, "not on the dense-table path");
   if (!dense_hi_) {
@@ -1022,10 +1064,10 @@ bool KpcEngine::sort_usable(const StreamState &st, size_t len, bool final_launch
 }
 
 bool KpcEngine::sort_process(StreamState &st, int mate, const uint8_t *dev, size_t len, uint64_t max_lines) {
-  // coarse buckets: the top bits of (key mod B); at most 2^20 of them
+  // coarse buckets: the top bits of (key mod B); at most 2^22 of them (16 MiB of counters: L2 resident)
   int lb = 0;
   while ((1ull << lb) < buckets_) ++lb;
-  const int lnb = lb < 20 ? lb : 20;
+  const int lnb = lb < 22 ? lb : 22;
   const uint32_t nb = 1u << lnb;
   const int cshift = lb - lnb;
   const size_t heavy_cap = 4096;

@@ -36,6 +36,7 @@ class KpcEngine {
   unsigned long long sink_buffer_used() const { return out_used_; }
   unsigned long long text_bytes() const { return text_bytes_; }
   void reset();
+  void reset_label(const std::string &label);
   int staging_slots() const { return kStagingSlots; }
   void *staging(int slot, size_t *capacity);
   void begin(int format);
@@ -48,6 +49,8 @@ class KpcEngine {
   unsigned long long kmers_counted();
   void dense_table(void **lo, void **hi, unsigned long long *nbins);
   unsigned long long dense_max();
+  bool dense_has_hi() const { return dense_hi_ != nullptr; }
+  unsigned long long count_newlines_device(const uint8_t *dev, size_t n);
   void dense_promote();
   void *native_stream() { return rt_stream_native(compute_); }
   void sync();

@@ -2,6 +2,7 @@
 // KPopCount-like driver that hands whole inputs to kpc_feed_device (the benchmark's entry point: consecutive launches
 // of one buffer, each reading the 16 bytes before it) through the C ABI of the emulation build.
 //   device_feed_driver <k> <DNA-ds|DNA-ss> <label> <fasta|single-end> file...
+// KPC_DRIVER_BATCH=1: one spectrum per file (labels <label>0, <label>1, ...) from ONE context: kpc_reset_label between them.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -21,7 +22,13 @@ int main(int argc, char **argv) {
   int dev = 0;
   if (kpc_create(&ctx, k, content, 16777216, argv[3], 1, &dev) != KPC_OK) { fprintf(stderr, "create: %s\n", kpc_error(ctx)); return 2; }
   kpc_set_sink(ctx, sink, nullptr);
+  const bool batch = getenv("KPC_DRIVER_BATCH") != nullptr;
   for (int a = 5; a < argc; ++a) {
+    if (batch) {
+      if (a > 5 && kpc_finish(ctx) != KPC_OK) { fflush(stdout); fprintf(stderr, "finish: %s\n", kpc_error(ctx)); return 2; }
+      const std::string lab = std::string(argv[3]) + std::to_string(a - 5);
+      if (kpc_reset_label(ctx, lab.c_str()) != KPC_OK) { fprintf(stderr, "reset_label: %s\n", kpc_error(ctx)); return 2; }
+    }
     FILE *f = fopen(argv[a], "rb");
     if (!f) { perror(argv[a]); return 2; }
     std::vector<char> raw;

@@ -30,14 +30,16 @@ def _worker(rank, world, port, tmp, big):
     data = subprocess.run([SYNTH, str(first), str(last - first), "3"], stdout=subprocess.PIPE, check=True).stdout
     lib = fastdense()
     t = dense_table(lib, data, K, threads=2)
-    if big:  # pretend one bin is close to wrapping on every rank
+    if big == 1:  # pretend one bin is close to wrapping on every rank
         t[5] = np.uint32(0xF0000000)
     lo = torch.from_numpy(t.view(np.int32).copy())
 
     def promote():
         return torch.from_numpy(t.astype(np.int64))
 
-    total = reduce_dense_tables(lo, promote, int(t.max()))
+    # big == 2: no bin is large, but rank 1 already keeps counts in its 64-bit side table (a folded bin): the reduce must
+    # be 64-bit on every rank all the same
+    total = reduce_dense_tables(lo, promote, int(t.max()), has_hi=(big == 2 and rank == 1))
     if total.dtype == torch.int32:
         res = total.numpy().view(np.uint32).astype(np.uint64)
     else:
@@ -48,22 +50,22 @@ def _worker(rank, world, port, tmp, big):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("big", [False, True])
+@pytest.mark.parametrize("big", [0, 1, 2])
 def test_two_rank_shard_and_reduce(tmp_path, big):
     subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
     from test_oracle_fastdense import SYNTH, dense_table, fastdense
-    port = 29500 + (os.getpid() % 2000) + (1 if big else 0)
+    port = 29500 + (os.getpid() % 2000) + big
     mp.spawn(_worker, args=(2, port, str(tmp_path), big), nprocs=2, join=True)
     whole = subprocess.run([SYNTH, "0", str(N_REC), "3"], stdout=subprocess.PIPE, check=True).stdout
     want = dense_table(fastdense(), whole, K).astype(np.uint64)
-    if big:
+    if big == 1:
         # what the per-rank tables summed to once bin 5 was overwritten on both ranks
         from kpop_b200.distributed import shard_records
         want[5] = 2 * 0xF0000000
     for r in range(2):
         got = np.load(tmp_path / f"res{r}_{int(big)}.npy")
         width = int(np.load(tmp_path / f"dtype{r}_{int(big)}.npy")[0])
-        assert width == (8 if big else 4)
+        assert width == (8 if big else 4)  # a side table on ONE rank (big == 2) widens the reduce on all of them
         assert np.array_equal(got, want)
 
 

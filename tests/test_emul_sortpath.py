@@ -77,3 +77,22 @@ def test_sort_path_is_taken_and_steps_aside(emul_bin, oracle_bin, tmp_path):
 
     assert launches(plain, "1") != launches(plain, "0")
     assert launches(heavy, "1") > launches(plain, "1")  # sort path tried first, then the hash table
+
+
+def test_batch_of_samples_through_one_context(emul_bin, oracle_bin, tmp_path):
+    """kpc_reset_label + kpc_feed_device on the hash-table path: many samples, one context (the C4 idiom), each spectrum equal
+    to what a separate `KPopCount -l <label>` run prints."""
+    from test_emul_fastpath import DRIVER
+    rng = random.Random(11)
+    files, want = [], b""
+    for i in range(5):
+        p = tmp_path / f"g{i}.fa"
+        p.write_bytes(repeats(rng) if i % 2 else b">g\n" + bytes(rng.choices(b"ACGT", k=700)) + (b"\n" if i != 2 else b""))
+        files.append(str(p))
+        rc, out, _ = run_cli(oracle_bin, ["-k", "21", "-l", f"S{i}", "-f", str(p)])
+        assert rc == 0
+        want += out
+    env = dict(os.environ, KPC_DRIVER_BATCH="1", KPC_EMUL_TILE="64x16")
+    rc, out, err = run_cli(DRIVER, ["21", "DNA-ds", "S", "fasta"] + files, env=env)
+    assert rc == 0, err
+    assert out == want
