@@ -57,7 +57,9 @@ typedef int (*kpc_sink_fn)(void *user, const char *bytes, size_t n);
 
 /* KIHF.create max_results_size + the functor's k check (bin/KPopCount.ml:35,239-249).
  * label "" selects -L behaviour exactly as in the reference (bin/KPopCount.ml:39,44).
- * n_devices must be 1 in this version (multi-GPU runs use one context per GPU, see kpc_dense_*). */
+ * n_devices > 1 (device_ids lists them): FASTQ inputs of dense-table runs (k <= 12 for DNA, one label) are cut into chunks
+ * at line starts and spread over the devices; kpc_finish adds the tables up on device_ids[0] over peer copies.  Anything
+ * else (FASTA, whose k-mers span lines; large k; -L) runs on device_ids[0] alone: results never depend on n_devices. */
 int kpc_create(kpc_ctx **out, int k, int content, long long max_results_size, const char *label, int n_devices,
                const int *device_ids);
 void kpc_destroy(kpc_ctx *ctx);

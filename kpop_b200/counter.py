@@ -47,12 +47,15 @@ _FORMATS = {"fasta": N.KPC_FASTA, "single-end": N.KPC_FASTQ_SE, "paired-end": N.
 
 
 class KMerCounter:
-    def __init__(self, k=12, content=Content.DNA_ds, max_results_size=16777216, label="", device=0, lib=None):
+    def __init__(self, k=12, content=Content.DNA_ds, max_results_size=16777216, label="", device=0, lib=None, devices=None):
+        """devices=[0, 1, ...]: several GPUs behind this one context (FASTQ inputs of dense-table runs are spread over
+        them, the tables are added up on the first one at finish); default: the single GPU `device`."""
         self._lib = lib or N.load()
         self._ctx = ctypes.c_void_p()
         self.k, self.content, self.max_results_size, self.label = k, content, max_results_size, label
-        dev = ctypes.c_int(device)
-        rc = self._lib.kpc_create(ctypes.byref(self._ctx), k, content, max_results_size, label.encode(), 1, ctypes.byref(dev))
+        ids = list(devices) if devices else [device]
+        dev = (ctypes.c_int * len(ids))(*ids)
+        rc = self._lib.kpc_create(ctypes.byref(self._ctx), k, content, max_results_size, label.encode(), len(ids), dev)
         if rc != N.KPC_OK:
             msg = self._lib.kpc_error(self._ctx).decode(errors="replace") if self._ctx else "allocation failure"
             self._lib.kpc_destroy(self._ctx)

@@ -5,11 +5,13 @@
 #include <string>
 
 #include "kpc_engine.h"
+#include "kpc_multi.h"
 #include "kpc_fastq.h"
 #include "kpc_synth.h"
 
 struct kpc_ctx {
-  KpcEngine *engine = nullptr;
+  KpcEngine *engine = nullptr;  // the (first) engine: owns the output, the final dump and everything that does not shard
+  KpcMulti *multi = nullptr;    // n_devices > 1: the engines of all devices and the dispatcher in front of them
   std::string error;
 };
 
@@ -20,6 +22,7 @@ template <class F>
 int guarded(kpc_ctx *ctx, F f) {
   if (!ctx || !ctx->engine) return KPC_E_ARG;
   try {
+    rt_set_device(ctx->engine->device());  // contexts on different GPUs, or a context driven from another thread
     f(*ctx->engine);
     return KPC_OK;
   } catch (const KpcError &e) {
@@ -47,8 +50,8 @@ int kpc_create(kpc_ctx **out, int k, int content, long long max_results_size, co
   kpc_ctx *ctx = new (std::nothrow) kpc_ctx();
   if (!ctx) return KPC_E_NOMEM;
   *out = ctx;  // returned even on failure so that kpc_error() can explain; kpc_destroy() frees it
-  if (n_devices != 1) {
-    ctx->error = "this version drives one GPU per context (one context per rank for multi-GPU runs)";
+  if (n_devices < 1 || n_devices > 64) {
+    ctx->error = "n_devices must be between 1 and 64";
     return KPC_E_ARG;
   }
   try {
@@ -58,7 +61,19 @@ int kpc_create(kpc_ctx **out, int k, int content, long long max_results_size, co
     cfg.max_results_size = max_results_size;
     cfg.label = label ? label : "";
     cfg.device = device_ids ? device_ids[0] : 0;
-    ctx->engine = new KpcEngine(cfg);
+    if (n_devices == 1) {
+      ctx->engine = new KpcEngine(cfg);
+      return KPC_OK;
+    }
+    std::vector<int> devs;
+    for (int i = 0; i < n_devices; ++i) {
+      const int d = device_ids ? device_ids[i] : i;
+      for (int o : devs)
+        if (o == d) throw KpcError(KPC_E_ARG, "the same device is listed twice");
+      devs.push_back(d);
+    }
+    ctx->multi = new KpcMulti(cfg, devs);
+    ctx->engine = &ctx->multi->first();
     return KPC_OK;
   } catch (const KpcError &e) {
     ctx->error = e.msg;
@@ -75,7 +90,8 @@ int kpc_create(kpc_ctx **out, int k, int content, long long max_results_size, co
 void kpc_destroy(kpc_ctx *ctx) {
   if (!ctx) return;
   try {
-    delete ctx->engine;
+    if (ctx->multi) delete ctx->multi;  // owns its engines
+    else delete ctx->engine;
   } catch (...) {
   }
   delete ctx;
@@ -95,38 +111,54 @@ int kpc_discard_text(kpc_ctx *ctx, int discard) {
 }
 unsigned long long kpc_text_bytes(const kpc_ctx *ctx) { return (ctx && ctx->engine) ? ctx->engine->text_bytes() : 0; }
 int kpc_reset(kpc_ctx *ctx) {
-  return guarded(ctx, [&](KpcEngine &e) { e.reset(); });
+  return guarded(ctx, [&](KpcEngine &e) { if (ctx->multi) ctx->multi->reset(); else e.reset(); });
 }
 int kpc_reset_label(kpc_ctx *ctx, const char *label) {
   if (!label) return KPC_E_ARG;
-  return guarded(ctx, [&](KpcEngine &e) { e.reset_label(label); });
+  return guarded(ctx, [&](KpcEngine &e) {
+    if (ctx->multi) throw KpcError(KPC_E_UNSUPPORTED, "kpc_reset_label on a multi-device context (samples shard with one context per device)");
+    e.reset_label(label);
+  });
 }
-int kpc_staging_slots(const kpc_ctx *ctx) { return (ctx && ctx->engine) ? ctx->engine->staging_slots() : 0; }
+int kpc_staging_slots(const kpc_ctx *ctx) {
+  if (!ctx || !ctx->engine) return 0;
+  return ctx->multi ? ctx->multi->staging_slots() : ctx->engine->staging_slots();
+}
 void *kpc_staging(kpc_ctx *ctx, int slot, size_t *capacity) {
   void *p = nullptr;
-  guarded(ctx, [&](KpcEngine &e) { p = e.staging(slot, capacity); });
+  guarded(ctx, [&](KpcEngine &e) { p = ctx->multi ? ctx->multi->staging(slot, capacity) : e.staging(slot, capacity); });
   return p;
 }
 int kpc_begin(kpc_ctx *ctx, int format) {
-  return guarded(ctx, [&](KpcEngine &e) { e.begin(format); });
+  return guarded(ctx, [&](KpcEngine &e) { if (ctx->multi) ctx->multi->begin(format); else e.begin(format); });
 }
 int kpc_feed(kpc_ctx *ctx, int mate, const void *bytes, size_t n, int eof) {
   if (n && !bytes) return KPC_E_ARG;
-  return guarded(ctx, [&](KpcEngine &e) { e.feed(mate, (const uint8_t *)bytes, n, eof != 0); });
+  return guarded(ctx, [&](KpcEngine &e) {
+    if (ctx->multi) ctx->multi->feed(mate, (const uint8_t *)bytes, n, eof != 0);
+    else e.feed(mate, (const uint8_t *)bytes, n, eof != 0);
+  });
 }
 int kpc_feed_device(kpc_ctx *ctx, int mate, const void *device_bytes, size_t n, int eof) {
   if (n && !device_bytes) return KPC_E_ARG;
-  return guarded(ctx, [&](KpcEngine &e) { e.feed_device(mate, (const uint8_t *)device_bytes, n, eof != 0); });
+  return guarded(ctx, [&](KpcEngine &e) {
+    if (ctx->multi && ctx->multi->sharding())
+      throw KpcError(KPC_E_UNSUPPORTED, "kpc_feed_device on a multi-device context (device inputs belong to one device: use one context per device)");
+    e.feed_device(mate, (const uint8_t *)device_bytes, n, eof != 0);
+  });
 }
 int kpc_set_pair_limit(kpc_ctx *ctx, long long n_pairs) {
-  return guarded(ctx, [&](KpcEngine &e) { e.set_pair_limit(n_pairs); });
+  return guarded(ctx, [&](KpcEngine &e) { if (ctx->multi) ctx->multi->set_pair_limit(n_pairs); else e.set_pair_limit(n_pairs); });
 }
-long long kpc_complete_pairs(const kpc_ctx *ctx) { return (ctx && ctx->engine) ? ctx->engine->complete_pairs() : -1; }
+long long kpc_complete_pairs(const kpc_ctx *ctx) {
+  if (!ctx || !ctx->engine) return -1;
+  return ctx->multi ? ctx->multi->complete_pairs() : ctx->engine->complete_pairs();
+}
 int kpc_end(kpc_ctx *ctx) {
-  return guarded(ctx, [&](KpcEngine &e) { e.end(); });
+  return guarded(ctx, [&](KpcEngine &e) { if (ctx->multi) ctx->multi->end(); else e.end(); });
 }
 int kpc_finish(kpc_ctx *ctx) {
-  return guarded(ctx, [&](KpcEngine &e) { e.finish(); });
+  return guarded(ctx, [&](KpcEngine &e) { if (ctx->multi) ctx->multi->finish(); else e.finish(); });
 }
 int kpc_kmers_counted(kpc_ctx *ctx, unsigned long long *out) {
   if (!out) return KPC_E_ARG;

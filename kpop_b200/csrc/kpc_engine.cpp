@@ -112,7 +112,10 @@ KpcEngine::KpcEngine(const KpcEngineConfig &cfg) : cfg_(cfg) {
     }
     st.err_line = (unsigned long long *)rt_dmalloc(sizeof(unsigned long long));
   }
-  for (int i = 0; i < kRing; ++i) ring_[i].computed = rt_event_create();
+  for (int i = 0; i < kRing; ++i) { ring_[i].computed = rt_event_create(); ring_[i].censused = rt_event_create(); }
+  d_shard_nl_ = (unsigned long long *)rt_dmalloc(kRing * sizeof(unsigned long long));
+  h_shard_nl_ = (unsigned long long *)rt_hmalloc(kRing * sizeof(unsigned long long));
+  h_shard_carry_ = (KpcStreamCarry *)rt_hmalloc(kRing * sizeof(KpcStreamCarry));
   for (int i = 0; i < kStagingSlots; ++i) staging_ev_[i] = rt_event_create();
 
   if (mode_ == DENSE) {
@@ -145,11 +148,13 @@ KpcEngine::~KpcEngine() {
   for (int i = 0; i < kRing; ++i) {
     if (ring_[i].buf) rt_dfree(ring_[i].buf);
     rt_event_destroy(ring_[i].computed);
+    rt_event_destroy(ring_[i].censused);
   }
   for (int i = 0; i < kStagingSlots; ++i) {
     if (staging_[i]) rt_hfree(staging_[i]);
     rt_event_destroy(staging_ev_[i]);
   }
+  rt_dfree(d_shard_nl_); rt_hfree(h_shard_nl_); rt_hfree(h_shard_carry_);
   rt_dfree(desc_); rt_dfree(tile_counter_); rt_dfree(d_tmp_); rt_hfree(h_tmp_);
   rt_dfree(scratch_); rt_dfree(scratch2_); rt_dfree(sort_buf_);
   if (h_out_) rt_hfree(h_out_);
@@ -537,7 +542,21 @@ void KpcEngine::feed_device(int mate, const uint8_t *dev, size_t n, bool eof) {
       const size_t sub = fq_launch_bytes_;
       for (size_t off = 0; off < cut; off += sub) run_launch(st, mate, dev + off, std::min(sub, cut - off), false, off > 0);
     } else {
-      run_launch(st, mate, dev, cut, false, false);
+      // the generic kernel: pieces of at most 1 GiB as well, so that the u32 counters can be folded in between; a piece of
+      // a FASTA stream must not end on a '>' that opens a line (the framing kernel looks one byte ahead there)
+      const size_t sub = (size_t)1 << 30;
+      size_t off = 0;
+      while (off < cut) {
+        size_t end = std::min(cut, off + sub);
+        while (format_ == KPC_FASTA && end < cut && end > off + 16) {
+          rt_d2h(h_tmp_ + 25, dev + end - 1, 1, compute_);
+          rt_stream_sync(compute_);
+          if (*(const uint8_t *)(h_tmp_ + 25) != '>') break;
+          end -= 16;
+        }
+        run_launch(st, mate, dev + off, end - off, false, false);
+        off = end;
+      }
     }
     const size_t w0 = n - win;
     st.at_line_start = cut > w0 ? tail[cut - w0 - 1] == '\n' : false;
@@ -554,6 +573,85 @@ void KpcEngine::feed_device(int mate, const uint8_t *dev, size_t n, bool eof) {
   run_launch(st, mate, slot.buf, tl, true, false);
   rt_event_record(slot.computed, compute_);
   slot.used = true;
+}
+
+// =================================================================================================
+// shards (kpc_multi.cpp): the stream of an input is cut at line starts by the caller, every shard goes to one device
+// =================================================================================================
+void KpcEngine::shard_begin(int format, bool with_header) {
+  const bool saved = discard_text_;
+  if (!with_header) discard_text_ = true;  // the label header is written once, by the first engine
+  begin(format);
+  discard_text_ = saved;
+}
+int KpcEngine::shard_upload(const Piece *pc, int npc, size_t len, rt_event ev1, rt_event ev2) {
+  if (mode_ != DENSE) throw KpcError(KPC_E_STATE, "internal: shards are a dense-table facility");
+  if (len > chunk_cap_ + 1) throw KpcError(KPC_E_STATE, "internal: shard larger than the staging size");
+  const int id = ring_next_;
+  RingSlot &slot = next_slot();
+  // the launch that used this buffer (and its pinned carry / census words) must be done: the host waits here, which also
+  // bounds how far it can run ahead of the device
+  if (slot.used) rt_event_sync(slot.computed);
+  size_t off = 0;
+  for (int i = 0; i < npc; ++i) {
+    if (!pc[i].n) continue;
+    rt_h2d(slot.buf + off, pc[i].p, pc[i].n, copy_);
+    off += pc[i].n;
+  }
+  if (ev1) rt_event_record(ev1, copy_);
+  if (ev2) rt_event_record(ev2, copy_);
+  rt_memset(d_shard_nl_ + id, 0, sizeof(unsigned long long), copy_);
+  kpc_k_count_newlines(slot.buf, len, d_shard_nl_ + id, copy_);
+  launches_ += len ? 1 : 0;
+  rt_d2h(h_shard_nl_ + id, d_shard_nl_ + id, sizeof(unsigned long long), copy_);
+  rt_event_record(slot.censused, copy_);
+  slot.len = len;
+  slot.used = true;
+  return id;
+}
+unsigned long long KpcEngine::shard_census(int id) {
+  rt_event_sync(ring_[id].censused);
+  return h_shard_nl_[id];
+}
+void KpcEngine::shard_count(int id, int mate, uint64_t lines_before, uint64_t max_lines) {
+  StreamState &st = streams_[mate];
+  RingSlot &slot = ring_[id];
+  KpcStreamCarry c;
+  memset(&c, 0, sizeof c);
+  c.s1 = kpc_s1_identity();
+  c.s1.count = lines_before;
+  c.kc = kpc_kc_identity();
+  c.kc.closed = 1;
+  c.last_byte = '\n';
+  h_shard_carry_[id] = c;  // (the slot's previous launch has been waited for by shard_upload)
+  rt_stream_wait(compute_, slot.censused);
+  rt_h2d(st.carry[st.cur], h_shard_carry_ + id, sizeof c, compute_);
+  st.at_line_start = true;
+  st.any = true;
+  max_lines_cap_ = max_lines;
+  run_launch(st, mate, slot.buf, slot.len, false, false);
+  max_lines_cap_ = ~0ull;
+  rt_event_record(slot.computed, compute_);
+}
+unsigned long long KpcEngine::shard_err_line(int mate) {
+  rt_d2h(h_tmp_ + mate, streams_[mate].err_line, sizeof(unsigned long long), compute_);
+  rt_stream_sync(compute_);
+  return h_tmp_[mate];
+}
+void KpcEngine::dense_add_remote(const unsigned long long *remote_hi, unsigned long long nbins, int remote_device) {
+  if (mode_ != DENSE || nbins != nbins_) throw KpcError(KPC_E_STATE, "internal: table shapes differ between devices");
+  dense_promote();  // everything of this engine in the 64-bit table as well
+  unsigned long long *tmp = (unsigned long long *)scratch(nbins_ * sizeof(unsigned long long));
+  rt_peer_copy(tmp, cfg_.device, remote_hi, remote_device, nbins_ * sizeof(unsigned long long), compute_);
+  kpc_k_add_u64(dense_hi_, tmp, nbins_, compute_);
+  ++launches_;
+  rt_stream_sync(compute_);
+}
+void KpcEngine::shard_end() {
+  if (!in_input_) throw KpcError(KPC_E_STATE, "kpc_end without kpc_begin");
+  in_input_ = false;
+  rt_stream_sync(copy_);
+  rt_stream_sync(compute_);
 }
 
 void KpcEngine::ensure_desc(uint64_t n_tiles) {
@@ -667,9 +765,12 @@ void KpcEngine::run_launch(StreamState &st, int mate, const uint8_t *dev, size_t
   if (format_ != KPC_FASTA) {
     if (final_launch) max_lines = final_line_cap(st, dev, len);
     if (pair_limit_ >= 0) max_lines = std::min<uint64_t>(max_lines, (uint64_t)pair_limit_ * 4);
+    max_lines = std::min<uint64_t>(max_lines, max_lines_cap_);
   }
   switch (mode_) {
     case DENSE: {
+      // every byte yields at most one window: fold the u32 counters BEFORE a launch that could carry one past 2^32
+      if (dense_since_fold_ + len >= (1ull << 31)) dense_fold_now();
       if (len && fq_usable() && (halo_ok || st.at_line_start) && len <= fq_launch_bytes_)
         fq_launch(st, dev, len, max_lines, halo_ok);
       else
@@ -799,19 +900,19 @@ void KpcEngine::finish() {
 // =================================================================================================
 // DENSE
 // =================================================================================================
-void KpcEngine::dense_after_launch(size_t len) {
-  // every byte yields at most one window: fold the u32 counters before any of them can wrap
-  dense_since_fold_ += len;
-  if (dense_since_fold_ >= (1ull << 31)) {
-    if (!dense_hi_) {
-      dense_hi_ = (unsigned long long *)rt_dmalloc(nbins_ * sizeof(unsigned long long));
-      rt_memset(dense_hi_, 0, nbins_ * sizeof(unsigned long long), compute_);
-    }
-    kpc_k_dense_fold(dense_lo_, dense_hi_, nbins_, compute_);
-    ++launches_;
-    dense_since_fold_ = 0;
+// bins at or above 2^31 move into the 64-bit side table.  Between two folds at most 2^31 windows are counted (checked
+// before every launch, launches are at most 1 GiB), so a bin that stays in the u32 table is below 2^31 + 2^31: no wrap.
+void KpcEngine::dense_fold_now() {
+  if (!dense_since_fold_) return;
+  if (!dense_hi_) {
+    dense_hi_ = (unsigned long long *)rt_dmalloc(nbins_ * sizeof(unsigned long long));
+    rt_memset(dense_hi_, 0, nbins_ * sizeof(unsigned long long), compute_);
   }
+  kpc_k_dense_fold(dense_lo_, dense_hi_, nbins_, compute_);
+  ++launches_;
+  dense_since_fold_ = 0;
 }
+void KpcEngine::dense_after_launch(size_t len) { dense_since_fold_ += len; }
 
 void KpcEngine::dense_finish() {
   // every key is its own bucket (4^k <= B): Hashtbl.iter order is ascending key order

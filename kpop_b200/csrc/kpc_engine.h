@@ -57,17 +57,34 @@ class KpcEngine {
   unsigned long long launches() const { return launches_; }
   void synth_fastq(void *dev_out, unsigned long long first, unsigned long long n, unsigned long long seed);
 
+  // ---- shards of a FASTQ stream counted on several devices (kpc_multi.cpp); dense-table runs only ----
+  struct Piece {
+    const uint8_t *p;
+    size_t n;
+  };
+  // copies the pieces (host memory) into the next ring buffer and counts its line feeds, all on the copy stream; returns
+  // the ring slot.  ev (optional) is recorded on the copy stream behind the copies.
+  int shard_upload(const Piece *pc, int npc, size_t len, rt_event ev1, rt_event ev2);
+  unsigned long long shard_census(int slot);  // waits for the upload; number of line feeds in the shard
+  // counts the shard: it starts a line, `lines_before` line feeds precede it in its stream; lines >= max_lines are ignored
+  void shard_count(int slot, int mate, uint64_t lines_before, uint64_t max_lines);
+  unsigned long long shard_err_line(int mate);  // first malformed line seen by this engine (~0 = none); synchronises
+  void shard_begin(int format, bool with_header);
+  void shard_end();
+  size_t chunk_cap() const { return chunk_cap_; }
+  void sync_copy() { rt_stream_sync(copy_); }
+  // this engine's table += a 64-bit table that lives on another device (peer copy into scratch, then an add kernel)
+  void dense_add_remote(const unsigned long long *remote_hi, unsigned long long nbins, int remote_device);
+  rt_event new_event() { rt_set_device(cfg_.device); return rt_event_create(); }
+
   enum Mode { DENSE, HASH, TUPLE };
   Mode mode() const { return mode_; }
+  int device() const { return cfg_.device; }
 
  private:
   static const int kStagingSlots = 3;
   static const int kRing = 3;
 
-  struct Piece {
-    const uint8_t *p;
-    size_t n;
-  };
   struct StreamState {  // one per mate of the current input
     uint64_t fed = 0;   // bytes handed to the device so far == stream offset of the next launch
     uint8_t *hold[2] = {nullptr, nullptr};  // pinned; kept-back tail of the stream (ping-pong: one may be in flight)
@@ -92,6 +109,8 @@ class KpcEngine {
     uint8_t *buf = nullptr;
     rt_event computed = nullptr;
     bool used = false;
+    rt_event censused = nullptr;  // shards: upload + line-feed census done
+    size_t len = 0;
   };
 
   // --- stream cutting ---
@@ -116,6 +135,7 @@ class KpcEngine {
 
   // --- mode specific ---
   void dense_after_launch(size_t len);
+  void dense_fold_now();
   void dense_finish();
   void hash_init();
   void hash_process(StreamState &st, int mate, const uint8_t *dev, size_t len, bool final_launch, uint64_t max_lines);
@@ -201,6 +221,10 @@ class KpcEngine {
   unsigned long long *d_hstat_ = nullptr;  // [0] distinct, [1] overflow
   uint64_t hdistinct_ = 0;
   uint64_t epoch_rank_lo_ = 0;  // windows with rank < this belong to already dumped epochs
+  uint64_t max_lines_cap_ = ~0ull;            // shards: upper line limit of the launch being issued
+  unsigned long long *d_shard_nl_ = nullptr;  // per ring slot: line feeds of the shard (device / pinned)
+  unsigned long long *h_shard_nl_ = nullptr;
+  KpcStreamCarry *h_shard_carry_ = nullptr;   // pinned, one per ring slot
   // sort path: a whole sample counted without the hash table (kpc_bucketsort.cuh); its entries wait here for finish()
   bool sort_enabled_ = true;
   bool sorted_pending_ = false;

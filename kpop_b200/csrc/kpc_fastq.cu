@@ -84,7 +84,8 @@ void kpc_fq_timing_read(double *partition_ms, double *count_ms, unsigned long lo
 template <bool DS, int KT>
 static void launch_partition(const KpcFqLaunch &L, rt_stream s) {
   auto kern = fq_partition_kernel<DS, KT>;
-  static int blocks_per_sm = 0;
+  static int blocks_per_sm_dev[64] = {0};  // the shared-memory attribute is per device: one slot per device
+  int &blocks_per_sm = blocks_per_sm_dev[rt_current_device() & 63];
   if (!blocks_per_sm) {
     FQ_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FqSmemT<FqProd>)));
     FQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, FqProd::NT, sizeof(FqSmemT<FqProd>)));
@@ -111,7 +112,8 @@ void kpc_fq_partition(const KpcFqLaunch &L, rt_stream s) {
 }
 
 void kpc_fq_count(const KpcFqLaunch &L, rt_stream s) {
-  static bool attr = false;
+  static bool attr_dev[64] = {false};
+  bool &attr = attr_dev[rt_current_device() & 63];
   if (!attr) {
     FQ_CUDA_CHECK(cudaFuncSetAttribute(fq_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (4 << 15) + 16));
     attr = true;

@@ -167,6 +167,13 @@ void kpc_k_dense_fold(uint32_t *lo, unsigned long long *hi, uint64_t nbins, rt_s
   dense_fold_kernel<<<ew_grid(nbins), 256, 0, cs(s)>>>(lo, hi, nbins);
   CUDA_CHECK(cudaGetLastError());
 }
+__global__ void add_u64_kernel(unsigned long long *dst, const unsigned long long *src, uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+void kpc_k_add_u64(unsigned long long *dst, const unsigned long long *src, uint64_t n, rt_stream s) {
+  add_u64_kernel<<<ew_grid(n), 256, 0, cs(s)>>>(dst, src, n);
+  CUDA_CHECK(cudaGetLastError());
+}
 void kpc_k_dense_promote(uint32_t *lo, unsigned long long *hi, uint64_t nbins, rt_stream s) {
   dense_promote_kernel<<<ew_grid(nbins), 256, 0, cs(s)>>>(lo, hi, nbins);
   CUDA_CHECK(cudaGetLastError());
@@ -385,7 +392,8 @@ void kpc_k_format(const unsigned long long *keys, const unsigned long long *coun
     return;
   }
   const size_t smem = (size_t)SCAN_BLK * (size_t)(hex_width + 22) + 32;  // 20 decimal digits at most
-  static size_t smem_set = 0;
+  static size_t smem_set_dev[64] = {0};
+  size_t &smem_set = smem_set_dev[rt_current_device() & 63];
   if (smem > smem_set) {
     CUDA_CHECK(cudaFuncSetAttribute(format_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
@@ -472,7 +480,8 @@ __global__ void __launch_bounds__(256) bucket_finalize_heavy_kernel(const KpcBuc
   kpc_bucket_finalize_heavy_body<256>(F, kpc_dyn_smem);
 }
 void kpc_k_bucket_finalize(const KpcBucketFinalize &F, rt_stream s) {
-  static bool attr = false;
+  static bool attr_dev[64] = {false};
+  bool &attr = attr_dev[rt_current_device() & 63];
   if (!attr) {
     CUDA_CHECK(cudaFuncSetAttribute(bucket_finalize_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(KpcBsHeavySmem)));

@@ -28,6 +28,8 @@ void kpc_k_count_newlines(const uint8_t *d, uint64_t n, unsigned long long *out,
 void kpc_k_dense_fold(uint32_t *lo, unsigned long long *hi, uint64_t nbins, rt_stream s);
 // hi[i] += lo[i]; lo[i] = 0   (used before a 64-bit reduction across GPUs)
 void kpc_k_dense_promote(uint32_t *lo, unsigned long long *hi, uint64_t nbins, rt_stream s);
+// dst[i] += src[i]   (sum of the 64-bit tables of two devices)
+void kpc_k_add_u64(unsigned long long *dst, const unsigned long long *src, uint64_t n, rt_stream s);
 // *out = max over bins of lo[i] + hi[i]
 void kpc_k_dense_max(const uint32_t *lo, const unsigned long long *hi, uint64_t nbins, unsigned long long *out,
                      rt_stream s);

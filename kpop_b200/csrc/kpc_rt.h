@@ -19,6 +19,8 @@ typedef struct rt_event_s *rt_event;
 const char *rt_backend_name();          // "cuda" for the product
 void rt_init(int device);               // selects the device, throws KpcError(KPC_E_CUDA) if there is none
 int rt_sm_count();
+void rt_set_device(int device);          // make `device` current on the calling thread (every ABI entry point does)
+int rt_current_device();
 void *rt_dmalloc(size_t n);
 void rt_dfree(void *p);
 void *rt_hmalloc(size_t n);             // pinned host memory
@@ -27,6 +29,8 @@ void rt_h2d(void *d, const void *h, size_t n, rt_stream s);
 void rt_d2h(void *h, const void *d, size_t n, rt_stream s);
 void rt_d2d(void *d, const void *src, size_t n, rt_stream s);
 void rt_memset(void *d, int v, size_t n, rt_stream s);
+// device memory of src_device -> device memory of dst_device (NVLink / PCIe peer copy), on a stream of the current device
+void rt_peer_copy(void *d, int dst_device, const void *src, int src_device, size_t n, rt_stream s);
 rt_stream rt_stream_create();
 void rt_stream_destroy(rt_stream s);
 void rt_stream_sync(rt_stream s);

@@ -30,6 +30,12 @@ void rt_init(int device) {
   g_sm_count = prop.multiProcessorCount;
 }
 int rt_sm_count() { return g_sm_count ? g_sm_count : 148; }
+void rt_set_device(int device) { RT_CHECK(cudaSetDevice(device)); }
+int rt_current_device() {
+  int d = 0;
+  RT_CHECK(cudaGetDevice(&d));
+  return d;
+}
 void *rt_dmalloc(size_t n) {
   void *p = nullptr;
   RT_CHECK(cudaMalloc(&p, n ? n : 1));
@@ -55,6 +61,9 @@ void rt_d2h(void *h, const void *d, size_t n, rt_stream s) {
 }
 void rt_d2d(void *d, const void *src, size_t n, rt_stream s) {
   if (n) RT_CHECK(cudaMemcpyAsync(d, src, n, cudaMemcpyDeviceToDevice, cs(s)));
+}
+void rt_peer_copy(void *d, int dst_device, const void *src, int src_device, size_t n, rt_stream s) {
+  if (n) RT_CHECK(cudaMemcpyPeerAsync(d, dst_device, src, src_device, n, cs(s)));
 }
 void rt_memset(void *d, int v, size_t n, rt_stream s) {
   if (n) RT_CHECK(cudaMemsetAsync(d, v, n, cs(s)));

@@ -188,10 +188,23 @@ int feed_files(kpc_ctx *ctx, const Input &in, std::string &err) {
 int run(const Params &P, Output &out, const std::vector<long long> &limits, size_t *bad_input, long long *pairs,
         std::string &err, bool &ctx_failed_early) {
   kpc_ctx *ctx = nullptr;
-  int dev = 0;
-  if (const char *e = getenv("KPC_DEVICE")) dev = atoi(e);
+  // which GPUs: KPC_DEVICES=0,1,... (several devices share the FASTQ inputs of a dense-table run), or KPC_DEVICE=n.
+  // The argv surface stays the reference's (it keeps -t / --threads reserved but commented out, bin/KPopCount.ml:93,187-194).
+  std::vector<int> devs;
+  if (const char *e = getenv("KPC_DEVICES")) {
+    for (const char *q = e; *q;) {
+      char *endp = nullptr;
+      const long v = strtol(q, &endp, 10);
+      if (endp == q) break;
+      devs.push_back((int)v);
+      q = *endp == ',' ? endp + 1 : endp;
+      if (*endp && *endp != ',') break;
+    }
+  }
+  if (devs.empty()) devs.push_back(getenv("KPC_DEVICE") ? atoi(getenv("KPC_DEVICE")) : 0);
   // the functor application of bin/KPopCount.ml:239-249: the k range check fires before the output exists
-  int rc = kpc_create(&ctx, (int)(P.k > 1000 ? 1000 : P.k), P.content, P.max_results_size, P.label.c_str(), 1, &dev);
+  int rc = kpc_create(&ctx, (int)(P.k > 1000 ? 1000 : P.k), P.content, P.max_results_size, P.label.c_str(), (int)devs.size(),
+                      devs.data());
   if (rc) {
     err = ctx ? kpc_error(ctx) : "out of memory";
     kpc_destroy(ctx);

@@ -94,6 +94,9 @@ void kpc_k_dense_fold(uint32_t *lo, unsigned long long *hi, uint64_t nbins, rt_s
   for (uint64_t i = 0; i < nbins; ++i)
     if (lo[i] >= 0x80000000u) { hi[i] += lo[i]; lo[i] = 0; }
 }
+void kpc_k_add_u64(unsigned long long *dst, const unsigned long long *src, uint64_t n, rt_stream) {
+  for (uint64_t i = 0; i < n; ++i) dst[i] += src[i];
+}
 void kpc_k_dense_promote(uint32_t *lo, unsigned long long *hi, uint64_t nbins, rt_stream) {
   for (uint64_t i = 0; i < nbins; ++i) { hi[i] += lo[i]; lo[i] = 0; }
 }

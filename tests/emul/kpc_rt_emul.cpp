@@ -11,6 +11,8 @@
 const char *rt_backend_name() { return "emulation"; }
 void rt_init(int) {}
 int rt_sm_count() { return 4; }
+void rt_set_device(int) {}
+int rt_current_device() { return 0; }
 void *rt_dmalloc(size_t n) { return calloc(1, n ? n + 64 : 64); }
 void rt_dfree(void *p) { free(p); }
 void *rt_hmalloc(size_t n) { return malloc(n ? n : 1); }
@@ -18,6 +20,7 @@ void rt_hfree(void *p) { free(p); }
 void rt_h2d(void *d, const void *h, size_t n, rt_stream) { if (n) memcpy(d, h, n); }
 void rt_d2h(void *h, const void *d, size_t n, rt_stream) { if (n) memcpy(h, d, n); }
 void rt_d2d(void *d, const void *s, size_t n, rt_stream) { if (n) memmove(d, s, n); }
+void rt_peer_copy(void *d, int, const void *s, int, size_t n, rt_stream) { if (n) memcpy(d, s, n); }
 void rt_memset(void *d, int v, size_t n, rt_stream) { if (n) memset(d, v, n); }
 rt_stream rt_stream_create() { return (rt_stream)malloc(1); }
 void rt_stream_destroy(rt_stream s) { free(s); }

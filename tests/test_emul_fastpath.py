@@ -45,7 +45,7 @@ def test_emul_fast_path_vs_oracle(emul_bin, oracle_bin, tmp_path, seed):
         rng = random.Random(7000 + 1000 * seed + c)
         k = rng.choice([4, 5, 6, 7, 8, 9, 10, 11, 12, 12, 12])
         content = rng.choice(["DNA-ds", "DNA-ds", "DNA-ss"])
-        kind = rng.choice(["fuzz", "fuzz", "regular", "ragged", "long"])
+        kind = rng.choice(["fuzz", "fuzz", "regular", "ragged", "long", "skew"])
 
         def gen():
             if kind == "fuzz":
@@ -54,6 +54,13 @@ def test_emul_fast_path_vs_oracle(emul_bin, oracle_bin, tmp_path, seed):
                 return regular(rng, rng.choice([1, 5, 30, 120]), rng.choice([20, 36, 100, 150]), crlf=rng.random() < 0.1)
             if kind == "ragged":
                 return regular(rng, rng.choice([5, 30, 100]), rng.choice([30, 150, 400]), ragged=True)
+            if kind == "skew":  # the same few k-mers over and over: buckets and queues overflow
+                out = bytearray()
+                for i in range(rng.choice([20, 100, 300])):
+                    unit = rng.choice([b"A", b"A", b"AC", b"ACG", b"T", b"GGGC"])
+                    ln = rng.choice([50, 150, 151])
+                    out += b"@s%d\n" % i + (unit * (ln // len(unit) + 1))[:ln] + b"\n+\n" + b"I" * ln + b"\n"
+                return bytes(out)
             return regular(rng, rng.choice([1, 3]), rng.choice([1000, 5000, 20000]))
 
         pe = rng.random() < 0.25
@@ -72,12 +79,18 @@ def test_emul_fast_path_vs_oracle(emul_bin, oracle_bin, tmp_path, seed):
         env["KPC_EMUL_TILE"] = "64x16"
         env["KPC_CHUNK_BYTES"] = str(rng.choice([4096, 5000, 8192, 70000, 1 << 20]))
         env["KPC_FQ_LAUNCH_BYTES"] = str(rng.choice([512, 2048, 1 << 20]))
+        devices = rng.choice([None, None, "0,1", "0,1,2"])  # several (emulated) devices behind one context
+        if devices:
+            env["KPC_DEVICES"] = devices
+        if rng.random() < 0.3:  # queues that overflow on small inputs: the count-in-place paths
+            env["KPC_FQ_QUEUE_PERMILLE"] = str(rng.choice([0, 100, 400]))
+            env["KPC_FQ_QUEUE_SLACK"] = str(rng.choice([0, 16, 64]))
         rc_o, out_o, _ = run_cli(oracle_bin, argv)
         if not pe and rng.random() < 0.5:
             rc_e, out_e, err_e = run_cli(DRIVER, [str(k), content, "x", "single-end", f1], env=env)
         else:
             rc_e, out_e, err_e = run_cli(emul_bin, argv, env=env)
-        ctx = f"seed={seed} case={c} kind={kind} env={env['KPC_EMUL_FQ']},{env['KPC_CHUNK_BYTES']},{env['KPC_FQ_LAUNCH_BYTES']} " \
+        ctx = f"seed={seed} case={c} kind={kind} env={env['KPC_EMUL_FQ']},{env['KPC_CHUNK_BYTES']},{env['KPC_FQ_LAUNCH_BYTES']},{env.get('KPC_DEVICES')} " \
               f"argv={' '.join(argv)}\n{err_e.decode(errors='replace')}"
         if rc_e == 2 and b"code -9" in err_e:
             skipped += 1  # KPC_E_UNSUPPORTED: lines longer than the staging size (documented refusal)

@@ -55,7 +55,12 @@ def test_emul_fuzz_vs_oracle(emul_bin, oracle_bin, tmp_path, seed):
         if fmt != "fasta":
             chunk = max(chunk, 4096)  # the FASTQ hold-back needs five lines per staging buffer
         rc_o, out_o, err_o = run_cli(oracle_bin, argv)
-        rc_e, out_e, err_e = run_cli(emul_bin, argv, env=emul_env(tile, str(chunk)))
+        env = emul_env(tile, str(chunk))
+        if rng.random() < 0.25:  # several (emulated) devices behind one context: results never depend on the device count
+            env["KPC_DEVICES"] = rng.choice(["0,1", "0,1,2"])
+            if fmt != "fasta":
+                env["KPC_CHUNK_BYTES"] = str(max(chunk, 8192))
+        rc_e, out_e, err_e = run_cli(emul_bin, argv, env=env)
         if rc_e == 2 and b"code -9" in err_e:  # KPC_E_UNSUPPORTED: refused explicitly, never a wrong answer
             refused.append((idx, err_e.decode(errors="replace").strip()[-160:]))
             continue
