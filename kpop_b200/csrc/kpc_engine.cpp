@@ -321,6 +321,18 @@ void KpcEngine::begin(int format) {
     }
   }
   if (sorted_pending_) sort_migrate();  // a further input for the same spectrum: continue on the hash table
+  // Paired-end files on the hash-table / -L paths: FASTQ.iter_pe hands out mate 1 and mate 2 of every pair in turn
+  // (Files.ml:222-250, 363-368), and both the dump rule (bin/KPopCount.ml:39) and Hashtbl's order depend on that order.
+  // The two byte streams are therefore woven into ONE single-end stream of complete pairs on the host (line splitting
+  // with memchr: these are not the throughput paths) and everything downstream sees single-end records.
+  pe_weave_ = format == KPC_FASTQ_PE && mode_ != DENSE;
+  if (pe_weave_) {
+    format = KPC_FASTQ_SE;
+    for (int m = 0; m < 2; ++m) { pe_q_[m].clear(); pe_scan_[m] = 0; pe_rec_end_[m] = 0; pe_lines_[m] = 0; pe_eof_[m] = false; }
+    pe_done_ = false;
+    pe_pairs_ = 0;
+    pe_out_.clear();
+  }
   format_ = format;
   in_input_ = true;
   reset_stream(streams_[0]);
@@ -378,6 +390,7 @@ KpcEngine::RingSlot &KpcEngine::next_slot() {
 void KpcEngine::feed(int mate, const uint8_t *bytes, size_t n, bool eof) {
   if (failed_) throw KpcError(KPC_E_STATE, "context is in a failed state");
   if (!in_input_) throw KpcError(KPC_E_STATE, "kpc_feed outside kpc_begin / kpc_end");
+  if (pe_weave_ && !pe_feeding_) { pe_enqueue(mate, bytes, n, eof); return; }
   if (mate < 0 || mate > 1 || (mate == 1 && format_ != KPC_FASTQ_PE)) throw KpcError(KPC_E_ARG, "bad mate index");
   StreamState &st = streams_[mate];
   if (st.eof) throw KpcError(KPC_E_STATE, "kpc_feed after eof");
@@ -447,6 +460,67 @@ void KpcEngine::feed(int mate, const uint8_t *bytes, size_t n, bool eof) {
     } else {
       rt_stream_sync(copy_);  // the caller may reuse its buffer as soon as we return
     }
+  }
+}
+
+// ---- paired-end weaving ---------------------------------------------------------------------------------------------
+void KpcEngine::pe_enqueue(int mate, const uint8_t *bytes, size_t n, bool eof) {
+  if (mate < 0 || mate > 1) throw KpcError(KPC_E_ARG, "bad mate index");
+  if (pe_eof_[mate]) throw KpcError(KPC_E_STATE, "kpc_feed after eof");
+  if (!pe_done_) pe_q_[mate].insert(pe_q_[mate].end(), bytes, bytes + n);
+  if (eof) {
+    pe_eof_[mate] = true;
+    // input_line returns a last line without line feed like any other one
+    if (!pe_done_ && !pe_q_[mate].empty() && pe_q_[mate].back() != '\n') pe_q_[mate].push_back('\n');
+  }
+  pe_pump(false);
+}
+// moves every complete PAIR of records (four lines from each mate) into the woven stream and feeds it on
+void KpcEngine::pe_pump(bool finishing) {
+  auto find_record = [&](int m) {  // end of the first complete record of queue m, 0 if there is none yet
+    if (pe_rec_end_[m]) return pe_rec_end_[m];
+    std::vector<uint8_t> &q = pe_q_[m];
+    while (pe_scan_[m] < q.size()) {
+      const void *p = memchr(q.data() + pe_scan_[m], '\n', q.size() - pe_scan_[m]);
+      if (!p) { pe_scan_[m] = q.size(); break; }
+      pe_scan_[m] = (size_t)((const uint8_t *)p - q.data()) + 1;
+      if (++pe_lines_[m] == 4) { pe_lines_[m] = 0; pe_rec_end_[m] = pe_scan_[m]; break; }
+    }
+    return pe_rec_end_[m];
+  };
+  size_t used[2] = {0, 0};
+  while (!pe_done_) {
+    // relative to what has been consumed in this call
+    size_t e0 = find_record(0), e1 = find_record(1);
+    if (!e0 || !e1) break;
+    pe_out_.insert(pe_out_.end(), pe_q_[0].begin() + used[0], pe_q_[0].begin() + e0);
+    pe_out_.insert(pe_out_.end(), pe_q_[1].begin() + used[1], pe_q_[1].begin() + e1);
+    used[0] = e0; used[1] = e1;
+    pe_rec_end_[0] = pe_rec_end_[1] = 0;
+    ++pe_pairs_;
+    if (pe_out_.size() >= chunk_cap_ / 2) {
+      pe_feeding_ = true;
+      try { feed(0, pe_out_.data(), pe_out_.size(), false); } catch (...) { pe_feeding_ = false; throw; }
+      pe_feeding_ = false;
+      pe_out_.clear();
+    }
+  }
+  for (int m = 0; m < 2; ++m) {
+    if (used[m]) {
+      pe_q_[m].erase(pe_q_[m].begin(), pe_q_[m].begin() + used[m]);
+      pe_scan_[m] -= used[m];
+    }
+  }
+  // a mate that has ended with no complete record left: iteration stops (a record of the other mate that was already
+  // read is dropped with it, Files.ml:228-247)
+  for (int m = 0; m < 2; ++m)
+    if (pe_eof_[m] && !find_record(m)) pe_done_ = true;
+  if (pe_done_) { pe_q_[0].clear(); pe_q_[1].clear(); pe_scan_[0] = pe_scan_[1] = 0; }
+  if ((pe_done_ || finishing) && !streams_[0].eof && (pe_eof_[0] && pe_eof_[1])) {
+    pe_feeding_ = true;
+    try { feed(0, pe_out_.data(), pe_out_.size(), true); } catch (...) { pe_feeding_ = false; throw; }
+    pe_feeding_ = false;
+    pe_out_.clear();
   }
 }
 
@@ -848,6 +922,11 @@ void KpcEngine::advance(StreamState &st, size_t len) {
 
 void KpcEngine::end() {
   if (!in_input_) throw KpcError(KPC_E_STATE, "kpc_end without kpc_begin");
+  if (pe_weave_) {
+    if (!pe_eof_[0] || !pe_eof_[1]) throw KpcError(KPC_E_STATE, "kpc_end before eof was signalled on every mate");
+    pe_pump(true);
+    complete_pairs_ = (long long)pe_pairs_;
+  }
   const int mates = format_ == KPC_FASTQ_PE ? 2 : 1;
   for (int m = 0; m < mates; ++m)
     if (!streams_[m].eof) throw KpcError(KPC_E_STATE, "kpc_end before eof was signalled on every mate");
@@ -877,7 +956,9 @@ void KpcEngine::end() {
     if (mode_ == TUPLE) tuple_flush(true);
     if (bad != ~0ull) {
       failed_ = true;
-      throw KpcError(KPC_E_MALFORMED_FASTQ, "On line " + std::to_string((bad + 1) * 4 * mates) + ": Malformed FASTQ file");
+      // woven pairs: record 2i and 2i + 1 are the mates of pair i; the reference names the last line of the pair
+      const uint64_t line = pe_weave_ ? (bad / 2 + 1) * 8 : (bad + 1) * 4 * mates;
+      throw KpcError(KPC_E_MALFORMED_FASTQ, "On line " + std::to_string(line) + ": Malformed FASTQ file");
     }
     rank_base_ += recs * mates;
   } else {
@@ -1074,7 +1155,7 @@ void KpcEngine::hash_process(StreamState &st, int mate, const uint8_t *dev, size
   run(lo, hi, 1);
   // a malformed FASTQ record ends the run there: nothing from that record on may influence the spill dumps
   if (format_ != KPC_FASTA && h_tmp_[2] != ~0ull && pair_limit_ < 0) {
-    const uint64_t bad_rec = h_tmp_[2] / 4;
+    const uint64_t bad_rec = pe_weave_ ? (h_tmp_[2] / 4) & ~1ull : h_tmp_[2] / 4;  // woven pairs: the whole pair goes
     const uint64_t mates = format_ == KPC_FASTQ_PE ? 2 : 1;
     const uint64_t stop = (rank_base_ + bad_rec * mates) << 32;
     run(stop, ~0ull, -1);
@@ -1113,10 +1194,7 @@ void KpcEngine::hash_process(StreamState &st, int mate, const uint8_t *dev, size
     }
     bool record_ends_here;
     if (format_ != KPC_FASTA) {
-      // Two mate files are scanned independently here, so the point in the pair order where the table reaches M
-      // cannot be reconstructed launch by launch: refuse rather than print a dump at the wrong record.
-      if (format_ == KPC_FASTQ_PE)
-        throw KpcError(KPC_E_UNSUPPORTED, "paired-end input whose table reaches -M on the hash path");
+      // (paired-end files arrive here woven into one stream of complete pairs: see begin())
       // the record of rstar is over once the line feed of its sequence line has been seen
       rt_d2h(h_tmp_ + 32, st.carry[st.cur ^ 1], sizeof(KpcStreamCarry), compute_);
       rt_stream_sync(compute_);
@@ -1314,6 +1392,7 @@ void KpcEngine::tuple_process(StreamState &st, int mate, const uint8_t *dev, siz
   } else {
     // all four lines seen (and, by the hold-back rule of choose_cut, the record is complete)
     st.final_recs = final_launch ? st.records : (cout.s1.count >> 2);
+    if (pe_weave_) st.final_recs &= ~1ull;  // a read is only handed out once its whole pair has been checked
   }
   tuple_flush(false);
 }
@@ -1329,6 +1408,9 @@ void KpcEngine::tuple_flush(bool input_done) {
     uint64_t bad = ~0ull;
     for (int m = 0; m < mates; ++m)
       if (h_tmp_[m] != ~0ull) bad = std::min<uint64_t>(bad, h_tmp_[m] / 4);
+    // woven pairs: a malformed mate takes its whole pair with it (FASTQ.iter_pe checks all eight lines before it hands
+    // out either read, Files.ml:241-243)
+    if (pe_weave_ && bad != ~0ull) bad &= ~1ull;
     if (input_done && mates == 2) {  // FASTQ.iter_pe stops at the shorter file
       const uint64_t pairs = std::min(streams_[0].records, streams_[1].records);
       fin[0] = std::min(fin[0], pairs);

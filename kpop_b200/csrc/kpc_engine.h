@@ -113,6 +113,20 @@ class KpcEngine {
     size_t len = 0;
   };
 
+  // --- paired-end input of hash-table / -L runs: the two mate streams are woven into one, pair by pair, on the host ---
+  void pe_enqueue(int mate, const uint8_t *bytes, size_t n, bool eof);
+  void pe_pump(bool finishing);
+  bool pe_weave_ = false;            // the current input is a woven pair of files (the engine sees single-end records)
+  std::vector<uint8_t> pe_q_[2];     // bytes of each mate not yet woven
+  size_t pe_scan_[2] = {0, 0};       // how far each queue has been searched for line feeds
+  size_t pe_rec_end_[2] = {0, 0};    // end of the first complete record in each queue (0 = none yet)
+  int pe_lines_[2] = {0, 0};         // line feeds of the record being completed
+  bool pe_eof_[2] = {false, false};
+  bool pe_feeding_ = false;          // the weaver itself is calling feed()
+  bool pe_done_ = false;             // one mate has ended: FASTQ.iter_pe stops there
+  std::vector<uint8_t> pe_out_;
+  uint64_t pe_pairs_ = 0;
+
   // --- stream cutting ---
   void reset_stream(StreamState &st);
   void hold_append(StreamState &st, const uint8_t *p, size_t n);

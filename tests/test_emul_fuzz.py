@@ -67,6 +67,6 @@ def test_emul_fuzz_vs_oracle(emul_bin, oracle_bin, tmp_path, seed):
         ctx = f"seed={seed} case={idx} tile={tile} chunk={chunk} argv={' '.join(argv)}\n{err_e.decode(errors='replace')}"
         assert rc_e == rc_o, ctx
         assert out_e == out_o, ctx
-    # refusals are counted, not hidden; the two shapes that remain are listed in DESIGN.md (section 8)
+    # refusals are counted, not hidden; the one shape that remains is listed in DESIGN.md (section 8)
     assert len(refused) <= n_cases // 8, refused
-    assert all("staging size" in m or "paired-end input whose table reaches -M" in m for _, m in refused), refused
+    assert all("staging size" in m for _, m in refused), refused
