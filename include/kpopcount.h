@@ -114,6 +114,21 @@ int kpc_count_newlines(kpc_ctx *ctx, const void *device_bytes, size_t n, unsigne
 /* 1 when some bin has been folded into the 64-bit side table (a reduction across ranks must then use kpc_dense_promote) */
 int kpc_dense_has_hi(kpc_ctx *ctx, int *has_hi);
 
+/* ---- multi-GPU, hash-table runs (large k): one sample cut into read chunks, one context per GPU / per rank -------------
+ * Every rank counts its records with insertion ranks that are valid for the WHOLE stream (kpc_set_record_base: index of
+ * the rank's first record), exports its distinct k-mers, the ranks exchange them by owner (a contiguous range of OCaml
+ * bucket indices per rank), every owner merges what it receives -- counts add, the smallest insertion rank wins -- and
+ * dumps its range: the concatenation in rank order is the spectrum (sparse merge).  Exact as long as the
+ * merged table stays below -M (no dump before the end); kpop_b200/distributed.py checks that. */
+int kpc_set_record_base(kpc_ctx *ctx, unsigned long long first_record);
+/* device arrays (u64) of the n distinct k-mers counted so far: key, count, insertion rank; slots whose key is ~0 are empty
+ * and must be skipped.  Valid until the next call on the context. */
+int kpc_hash_export(kpc_ctx *ctx, void **keys, void **counts, void **ranks, unsigned long long *n_slots);
+/* inserts n entries (device arrays, u64) into the table, after emptying it when clear_first != 0: equal keys merge */
+int kpc_hash_import(kpc_ctx *ctx, const void *keys, const void *counts, const void *ranks, unsigned long long n, int clear_first);
+/* B, the bucket count of OCaml's Hashtbl for this run (the dump is ordered by key mod B) */
+unsigned long long kpc_bucket_count(const kpc_ctx *ctx);
+
 /* empty the tables and forget every input, keeping all allocations (a context can then be used for another run) */
 int kpc_reset(kpc_ctx *ctx);
 /* the same, and the next run gets this spectrum label (bin/KPopCount.ml:158-172).  Batch use: one context serves many

@@ -24,6 +24,11 @@ PROTOTYPES = {
     "kpc_staging": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]),
     "kpc_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "kpc_feed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
+    "kpc_set_record_base": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_ulonglong]),
+    "kpc_hash_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                       ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_ulonglong)]),
+    "kpc_hash_import": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_int]),
+    "kpc_bucket_count": (ctypes.c_ulonglong, [ctypes.c_void_p]),
     "kpc_count_newlines": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_ulonglong)]),
     "kpc_dense_has_hi": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]),
     "kpc_reset_label": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),

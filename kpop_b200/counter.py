@@ -184,6 +184,26 @@ class KMerCounter:
         self._check(self._lib.kpc_dense_max(self._ctx, ctypes.byref(out)))
         return out.value
 
+    def set_record_base(self, first_record):
+        self._check(self._lib.kpc_set_record_base(self._ctx, first_record))
+
+    def hash_export(self):
+        """(keys ptr, counts ptr, ranks ptr, slots) of the distinct k-mers counted so far (device arrays of u64)."""
+        k, c, r = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        n = ctypes.c_ulonglong(0)
+        self._check(self._lib.kpc_hash_export(self._ctx, ctypes.byref(k), ctypes.byref(c), ctypes.byref(r), ctypes.byref(n)))
+        return k.value or 0, c.value or 0, r.value or 0, int(n.value)
+
+    def hash_import(self, keys_ptr, counts_ptr, ranks_ptr, n, clear_first=True):
+        self._check(self._lib.kpc_hash_import(self._ctx, ctypes.c_void_p(keys_ptr), ctypes.c_void_p(counts_ptr),
+                                              ctypes.c_void_p(ranks_ptr), n, 1 if clear_first else 0))
+
+    def bucket_count(self):
+        return int(self._lib.kpc_bucket_count(self._ctx))
+
+    def backend(self):
+        return self._lib.kpc_backend().decode()
+
     def dense_has_hi(self):
         v = ctypes.c_int(0)
         self._check(self._lib.kpc_dense_has_hi(self._ctx, ctypes.byref(v)))

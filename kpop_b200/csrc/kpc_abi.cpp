@@ -172,6 +172,20 @@ int kpc_dense_max(kpc_ctx *ctx, unsigned long long *max_count) {
   if (!max_count) return KPC_E_ARG;
   return guarded(ctx, [&](KpcEngine &e) { *max_count = e.dense_max(); });
 }
+int kpc_set_record_base(kpc_ctx *ctx, unsigned long long first_record) {
+  return guarded(ctx, [&](KpcEngine &e) { e.set_record_base(first_record); });
+}
+int kpc_hash_export(kpc_ctx *ctx, void **keys, void **counts, void **ranks, unsigned long long *n_slots) {
+  if (!keys || !counts || !ranks || !n_slots) return KPC_E_ARG;
+  return guarded(ctx, [&](KpcEngine &e) { e.hash_export(keys, counts, ranks, n_slots); });
+}
+int kpc_hash_import(kpc_ctx *ctx, const void *keys, const void *counts, const void *ranks, unsigned long long n, int clear_first) {
+  if (n && (!keys || !counts || !ranks)) return KPC_E_ARG;
+  return guarded(ctx, [&](KpcEngine &e) {
+    e.hash_import((const unsigned long long *)keys, (const unsigned long long *)counts, (const unsigned long long *)ranks, n, clear_first != 0);
+  });
+}
+unsigned long long kpc_bucket_count(const kpc_ctx *ctx) { return (ctx && ctx->engine) ? ctx->engine->bucket_count() : 0; }
 int kpc_count_newlines(kpc_ctx *ctx, const void *device_bytes, size_t n, unsigned long long *count) {
   if (!count || (n && !device_bytes)) return KPC_E_ARG;
   return guarded(ctx, [&](KpcEngine &e) { *count = e.count_newlines_device((const uint8_t *)device_bytes, n); });

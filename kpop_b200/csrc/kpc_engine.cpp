@@ -1295,6 +1295,52 @@ bool KpcEngine::sort_process(StreamState &st, int mate, const uint8_t *dev, size
   return true;
 }
 
+void KpcEngine::set_record_base(unsigned long long first_record) {
+  if (in_input_ || header_done_) throw KpcError(KPC_E_STATE, "kpc_set_record_base after the first kpc_begin");
+  rank_base_ = first_record;
+}
+void KpcEngine::hash_export(void **keys, void **counts, void **ranks, unsigned long long *n_slots) {
+  if (mode_ != HASH) throw KpcError(KPC_E_STATE, "not on the hash-table path");
+  if (in_input_) throw KpcError(KPC_E_STATE, "kpc_hash_export inside an input");
+  if (sorted_pending_) {  // the sort path's entries (fillers carry the empty key)
+    rt_stream_sync(compute_);
+    *keys = skeys_; *counts = scounts_; *ranks = sranks_; *n_slots = sorted_slots_;
+    return;
+  }
+  if (!hcap_) { *keys = *counts = *ranks = nullptr; *n_slots = 0; return; }
+  const size_t need = (size_t)std::min<uint64_t>(hcap_, hdistinct_ + 1);
+  unsigned long long *ok = (unsigned long long *)scratch(need * 24 + kpc_k_scan_scratch_bytes(hcap_) + 1024);
+  unsigned long long *oc = ok + need, *orr = oc + need;
+  kpc_k_hash_extract(hkeys_, hcounts_, hranks_, hcap_, ok, oc, orr, d_tmp_ + 6, orr + need, compute_);
+  launches_ += 3;
+  rt_d2h(h_tmp_ + 6, d_tmp_ + 6, 8, compute_);
+  rt_stream_sync(compute_);
+  *keys = ok; *counts = oc; *ranks = orr; *n_slots = h_tmp_[6];
+}
+void KpcEngine::hash_import(const unsigned long long *keys, const unsigned long long *counts, const unsigned long long *ranks,
+                            unsigned long long n, bool clear_first) {
+  if (mode_ != HASH) throw KpcError(KPC_E_STATE, "not on the hash-table path");
+  if (in_input_) throw KpcError(KPC_E_STATE, "kpc_hash_import inside an input");
+  if (sorted_pending_ && !clear_first) sort_migrate();
+  if (clear_first) {
+    sorted_pending_ = false;
+    if (hcap_) { kpc_k_hash_clear(hkeys_, hcounts_, hranks_, hcap_, compute_); ++launches_; }
+    rt_memset(d_hstat_, 0, 2 * sizeof(unsigned long long), compute_);
+    hdistinct_ = 0;
+  }
+  header_done_ = true;  // a context that only merges still owes its part of the dump
+  hash_ensure_capacity(hdistinct_ + n + 16);
+  if (n) {
+    KpcHashSink nw = hash_sink(0, ~0ull, 1);
+    kpc_k_hash_rehash(keys, counts, ranks, n, nw, compute_);
+    ++launches_;
+  }
+  rt_d2h(h_tmp_, d_hstat_, 2 * sizeof(unsigned long long), compute_);
+  rt_stream_sync(compute_);
+  if (h_tmp_[1]) throw KpcError(KPC_E_NOMEM, "internal: hash table overflow");
+  hdistinct_ = h_tmp_[0];
+}
+
 // the sample counted by the sort path is followed by another input: its entries go into the hash table
 void KpcEngine::sort_migrate() {
   sorted_pending_ = false;

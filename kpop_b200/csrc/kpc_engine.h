@@ -50,6 +50,12 @@ class KpcEngine {
   void dense_table(void **lo, void **hi, unsigned long long *nbins);
   unsigned long long dense_max();
   bool dense_has_hi() const { return dense_hi_ != nullptr; }
+  // hash-table runs sharded over several contexts (kpop_b200/distributed.py: sparse merge)
+  void set_record_base(unsigned long long first_record);
+  void hash_export(void **keys, void **counts, void **ranks, unsigned long long *n_slots);
+  void hash_import(const unsigned long long *keys, const unsigned long long *counts, const unsigned long long *ranks,
+                   unsigned long long n, bool clear_first);
+  unsigned long long bucket_count() const { return buckets_; }
   unsigned long long count_newlines_device(const uint8_t *dev, size_t n);
   void dense_promote();
   void *native_stream() { return rt_stream_native(compute_); }

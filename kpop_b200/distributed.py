@@ -121,14 +121,21 @@ def record_aligned_ranges(size, lo, hi, n_newlines, first_newlines, byte_before_
         k = (-lines_before) % 4 or 4           # the k-th line feed of the range is followed by the start of a record
         if len(first_newlines) >= k:
             start = first_newlines[k - 1] + 1
+    # index of the record that starts at `start`: the line feeds before it, over four
+    first_line = 0
+    if rank > 0 and start >= 0:
+        first_line = lines_before if start == lo else lines_before + ((-lines_before) % 4 or 4)
     starts = [x - 1 for x in _all_gather_i64(start + 1, rank, world_size, group)]
-    nxt = size
+    first_lines = _all_gather_i64(first_line, rank, world_size, group)
+    total_lines = sum(counts)
+    nxt, nxt_line = size, total_lines
     ends = [0] * world_size
     for r in range(world_size - 1, -1, -1):    # ranks without a boundary in their range take nothing
         if starts[r] < 0:
-            starts[r] = nxt
+            starts[r], first_lines[r] = nxt, nxt_line
         ends[r] = nxt
-        nxt = starts[r]
+        nxt, nxt_line = starts[r], first_lines[r]
+    record_aligned_ranges.first_record = first_lines[rank] // 4   # (side channel for count_fastq_sharded_sparse)
     return starts[rank], ends[rank]
 
 
@@ -251,3 +258,116 @@ def count_fastq_sharded(path, k=12, label="sample", device=None, group=None, chu
             kc.finish()
             text = kc.take_text()
     return text
+
+
+# ------------------------------------------------------------------------------------------------------------
+# sparse merge: ONE large-k sample on all the GPUs (last bullet)
+# ------------------------------------------------------------------------------------------------------------
+def _u64_view(counter, ptr, n):
+    """int64 torch view of n u64 words the library owns (device memory; host memory under the test-only emulation)."""
+    if n == 0 or not ptr:
+        return torch.zeros(0, dtype=torch.int64, device="cuda" if counter.backend() == "cuda" else "cpu")
+    if counter.backend() == "cuda":
+        return torch.as_tensor(DeviceArray(ptr, n, "<i8"), device="cuda")
+    import ctypes
+    import numpy as np
+    return torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_int64)), shape=(n,)))
+
+
+def bucket_owner(keys_i64, n_buckets, world_size):
+    """Owner rank of every key: OCaml bucket indices (key mod B) are cut into world_size contiguous ranges, so that the
+    dumps of the owners, concatenated in rank order, are in Hashtbl.iter order."""
+    return ((keys_i64 & (n_buckets - 1)) * world_size) // n_buckets
+
+
+def exchange_entries(keys, counts, ranks, n_buckets, rank, world_size, group=None):
+    """Every entry travels to the rank that owns its bucket (all-to-all with the sizes exchanged first)."""
+    if world_size == 1:
+        return keys, counts, ranks
+    owner = bucket_owner(keys, n_buckets, world_size)
+    order = torch.argsort(owner, stable=True)
+    send_sizes = torch.bincount(owner, minlength=world_size).to(torch.int64)
+    recv_sizes = torch.zeros_like(send_sizes)
+    dist.all_to_all_single(recv_sizes, send_sizes, group=group)
+    ss, rs = [int(x) for x in send_sizes.tolist()], [int(x) for x in recv_sizes.tolist()]
+    out = []
+    for t in (keys, counts, ranks):
+        src = t[order].contiguous()
+        dst = torch.empty(sum(rs), dtype=torch.int64, device=t.device)
+        if dist.get_backend(group) == "gloo":   # gloo has no all_to_all_single with uneven splits on every version: send / recv
+            reqs = []
+            so = ro = 0
+            for r in range(world_size):
+                if r == rank:
+                    dst[ro: ro + rs[r]] = src[so: so + ss[r]]
+                else:
+                    if ss[r]:
+                        reqs.append(dist.isend(src[so: so + ss[r]].clone(), r, group=group))
+                    if rs[r]:
+                        reqs.append(dist.irecv(dst[ro: ro + rs[r]], r, group=group))
+                so += ss[r]
+                ro += rs[r]
+            for q in reqs:
+                q.wait()
+        else:
+            dist.all_to_all_single(dst, src, rs, ss, group=group)
+        out.append(dst)
+    return tuple(out)
+
+
+def count_fastq_sharded_sparse(path, k=21, label="sample", device=0, group=None, max_results_size=16777216, lib=None,
+                               chunk_bytes=32 << 20):
+    """KPopCount -k K -l LABEL -s PATH for k > 12 (hash-table path) on all the ranks of the process group.
+
+    Every rank counts its record-aligned byte range of the file with insertion ranks that are valid for the whole file,
+    exports its distinct k-mers, the entries travel to the rank that owns their OCaml bucket, the owners merge them on the
+    device (counts add, the smallest insertion rank wins: kpc_hash_import) and dump their bucket range; rank 0 returns the
+    concatenation -- the bytes one KPopCount process prints -- and the others None.  Raises when the merged table could
+    reach -M (the reference would then dump in the middle of the stream, which does not shard)."""
+    from .counter import KMerCounter, KPopCountError
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    start, end = shard_fastq_byte_range(path, group)
+    first_record = record_aligned_ranges.first_record
+    err, text = None, None
+    with KMerCounter(k=k, label=label, max_results_size=max_results_size, device=device, lib=lib) as kc:
+        n_slots = 0
+        try:
+            kc.set_record_base(first_record)
+            kc.begin("single-end")
+            with open(path, "rb") as f:
+                f.seek(start)
+                pos = start
+                if end == start:
+                    kc.feed(b"", eof=True)
+                while pos < end:
+                    b = f.read(min(chunk_bytes, end - pos))
+                    pos += len(b)
+                    kc.feed(b, eof=(pos >= end))
+            kc.end()
+            kp, cp, rp, n_slots = kc.hash_export()
+        except Exception as e:  # noqa: BLE001 -- shared with the other ranks below
+            err = e
+        _raise_together(err, rank, world, group)
+        keys, counts, ranks = (_u64_view(kc, p, n_slots) for p in (kp, cp, rp))
+        live = keys != -1                       # empty slots carry the key ~0
+        keys, counts, ranks = keys[live], counts[live], ranks[live]
+        total = sum(_all_gather_i64(int(keys.numel()), rank, world, group))
+        if total >= max_results_size:
+            raise KPopCountError(-9, "the merged table could reach -M: the reference would dump in the middle of the stream")
+        keys, counts, ranks = exchange_entries(keys, counts, ranks, kc.bucket_count(), rank, world, group)
+        keys, counts, ranks = keys.contiguous(), counts.contiguous(), ranks.contiguous()
+        if keys.is_cuda:
+            torch.cuda.synchronize()
+        kc.take_text()
+        kc.hash_import(keys.data_ptr(), counts.data_ptr(), ranks.data_ptr(), int(keys.numel()), clear_first=True)
+        kc.finish()
+        mine = kc.take_text()
+    header = ("\t%s\n" % label).encode()
+    if mine.startswith(header):
+        mine = mine[len(header):]
+    if world == 1:
+        return header + mine
+    parts = [None] * world
+    dist.all_gather_object(parts, mine, group=group)
+    return header + b"".join(parts) if rank == 0 else None

@@ -120,3 +120,44 @@ def test_fastq_file_is_cut_at_record_boundaries(tmp_path, world):
         total += dense_table(lib, data[a:b], K).astype(np.uint64)
     assert np.array_equal(total, dense_table(lib, data, K).astype(np.uint64))
     assert sum(1 for a, b in ranges if b > a) == world   # nobody idles on this input
+
+
+# ---- sparse merge (last bullet): one large-k sample on two ranks, emulated library on the CPU -----------------
+def _sparse_worker(rank, world, port, path, tmp, k):
+    sys.path.insert(0, ROOT)
+    from kpop_b200 import _native
+    from kpop_b200.distributed import count_fastq_sharded_sparse
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["KPC_EMUL_TILE"] = "64x16"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = _native.load(os.path.join(ROOT, "tests", "emul", "_build", "libkpopcount_emul.so"))
+    text = count_fastq_sharded_sparse(path, k=k, label="x", lib=lib, chunk_bytes=20000)
+    if rank == 0:
+        with open(os.path.join(tmp, "sparse.txt"), "wb") as f:
+            f.write(text)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,k", [(2, 21), (3, 13)])
+def test_sparse_merge_of_a_sharded_sample_equals_one_process(tmp_path, world, k):
+    """Each rank counts its shard on the hash-table path with stream-wide insertion ranks; the entries are exchanged by
+    bucket owner, merged (kpc_hash_import) and dumped per owner: the concatenation must be what ONE KPopCount prints,
+    order included (repeated reads make the same k-mer first appear on different ranks)."""
+    import random
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "emul")], check=True)
+    rng = random.Random(17 + world)
+    reads = [bytes(rng.choices(b"ACGTN", weights=[30, 30, 30, 30, 1], k=rng.choice([40, 80, 120]))) for _ in range(120)]
+    recs = []
+    for i in range(1500):
+        s = rng.choice(reads)                   # heavy repetition: the same k-mers on every shard
+        recs.append(b"@r%d\n%s\n+\n%s\n" % (i, s, bytes(rng.choice(b"@+I") for _ in range(len(s)))))
+    path = tmp_path / "reads.fq"
+    path.write_bytes(b"".join(recs))
+    port = 33000 + (os.getpid() % 2000) + world
+    mp.spawn(_sparse_worker, args=(world, port, str(path), str(tmp_path), k), nprocs=world, join=True)
+    want = subprocess.run([os.path.join(ORACLE_DIR, "_build", "kpopcount_oracle"), "-k", str(k), "-l", "x", "-s", str(path)],
+                          stdout=subprocess.PIPE, check=True).stdout
+    assert (tmp_path / "sparse.txt").read_bytes() == want

@@ -21,12 +21,16 @@ def _n_gpus():
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("world", [2])
-def test_one_fastq_file_on_two_gpus(world, oracle_bin):
-    port = 29700 + os.getpid() % 200
+@pytest.mark.parametrize("tool,arg", [("mgpu_file_check.py", "300000"), ("mgpu_sparse_check.py", "60000")],
+                         ids=["dense_table_reduce", "sparse_merge"])
+def test_one_fastq_file_on_two_gpus(tool, arg, oracle_bin):
+    """Read-chunk sharding of one file on two ranks: dense tables + NCCL reduce (k = 12), and the sparse merge of the
+    hash-table path (k = 21: entries exchanged by bucket owner, merged on the device)."""
+    world = 2
+    port = 29700 + os.getpid() % 200 + (7 if "sparse" in tool else 0)
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
-                        os.path.join(ROOT, "tools", "mgpu_file_check.py"), "300000"],
+                        os.path.join(ROOT, "tools", tool), arg],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
     out = p.stdout.decode(errors="replace")
     assert p.returncode == 0, out[-2000:]
