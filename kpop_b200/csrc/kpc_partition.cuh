@@ -39,6 +39,9 @@
 #ifndef FQ_APPEND_GROUP
 #define FQ_APPEND_GROUP 4   // shared-memory atomics issued back to back per group of windows (1, 2 or 4)
 #endif
+#ifndef FQ_PADFILL
+#define FQ_PADFILL 1        // 1: windows that are not valid take a bucket position that already reads as padding; 0: they
+#endif                      //    count into per-lane dummy counters instead (one SEL per window, no padding in the queues)
 #ifndef FQ_L2HINTS
 #define FQ_L2HINTS 1        // census loads evict_last, the tile's bulk copy evict_first
 #endif
@@ -73,6 +76,7 @@ struct FqSmemT {
   alignas(128) uint8_t raw[FQ_HALO + G::TB + 48];  // raw[16 + i] = tile byte i
   alignas(16) uint16_t bucket[FQ_BUCKET_ENTRIES + FQ_BPAD * FQ_MAXSLICES + 2 * FQ_CHUNK];  // slice s owns [s * (cap + FQ_BPAD), + cap)
   uint32_t fill[FQ_MAXSLICES];                    // entries in the bucket (may run past cap while appending)
+  uint32_t dummy[32];                             // FQ_PADFILL == 0: where the appends of windows that are not valid count
   uint32_t uinfo[G::MAXUNITS];                    // unit -> first window end (low half) | end of its line (high half)
   uint16_t rowS[G::MAXROWS + 2], rowE[G::MAXROWS + 2];  // first byte / line feed of every sequence line, + FQ_PBIAS
   uint32_t wtot[32], wtot2[64];                   // warp totals: block scans / census of the next tile (two slots)
@@ -207,6 +211,9 @@ KP_DEV void fq_flush_reserve(FqSmemT<G> &S, const KpcFqLaunch &p, FqOwner<G> &ow
       if (f > cap) f = cap;
       // whole chunks; the CTA is leaving: the last chunk goes out as it is (the entries behind the fill are FQ_PAD)
       const uint32_t n = final ? (f + FQ_CHUNK - 1u) & ~(uint32_t)(FQ_CHUNK - 1) : f & ~(uint32_t)(FQ_CHUNK - 1);
+#if !FQ_PADFILL
+      if (final) for (uint32_t e = f; e < n; ++e) S.bucket[s * (cap + FQ_BPAD) + e] = FQ_PAD;
+#endif
       S.fill[s] = f > n ? f - n : 0u;
       own.n[i] = n;
       if (n) own.g[i] = atomicAdd(p.qcursor + s, n);
@@ -243,10 +250,14 @@ KP_DEV void fq_flush_copy(FqSmemT<G> &S, const KpcFqLaunch &p, const FqOwner<G> 
           if (en != FQ_PAD) atomicAdd(p.table + fq_key_of(s, en, lo, sb, lomask), 1u);
         }
       }
+#if FQ_PADFILL
       src[c >> 3] = pad4;  // what has been copied reads as padding again
       src[(c >> 3) + 1] = pad4;
+#endif
     }
+#if FQ_PADFILL
     if (my_n < cap) { src[my_n >> 3] = pad4; src[(my_n >> 3) + 1] = pad4; }
+#endif
     src[0] = r0;
     src[1] = r1;
   }
@@ -271,7 +282,8 @@ KP_DEV uint32_t fq_top_word(uint32_t hi, uint32_t lo, int s) {
 // a valid window is cleared in `pending` once the key sits in its bucket.
 template <bool DS, class SmemT>
 KP_DEV void fq_append4_k12(SmemT &S, uint32_t hi24, uint32_t lo32, uint32_t rhi, uint32_t rlo, int jw0, uint32_t ok,
-                           uint32_t &pending) {
+                           uint32_t &pending, uint32_t dummy_off) {
+  (void)dummy_off;
   constexpr int GR = FQ_APPEND_GROUP;
   uint32_t kk[GR], sl4[GR], pos[GR];
 #pragma unroll
@@ -282,8 +294,14 @@ KP_DEV void fq_append4_k12(SmemT &S, uint32_t hi24, uint32_t lo32, uint32_t rhi,
     sl4[i] = (kk[i] >> 14) & 0x7FCu;                              // 4 * slice
   }
 #pragma unroll
-  for (int i = 0; i < GR; ++i)
+  for (int i = 0; i < GR; ++i) {
+#if FQ_PADFILL
     pos[i] = atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(S.fill) + sl4[i]), 1u);
+#else
+    const bool valid = (ok & (1u << (FQ_W - 1 - (jw0 + i)))) != 0u;
+    pos[i] = atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(S.fill) + (valid ? sl4[i] : dummy_off)), 1u);
+#endif
+  }
 #pragma unroll
   for (int i = 0; i < GR; ++i) {
     const uint32_t bit = 1u << (FQ_W - 1 - (jw0 + i));
@@ -374,6 +392,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
   const uint32_t NS = KT == 12 ? 512u : p.n_slices;
   const uint32_t smask = NS - 1u, lomask = (1u << slo) - 1u;
   const uint32_t cap = (uint32_t)FQ_BUCKET_ENTRIES / NS;  // bucket capacity per slice: a multiple of FQ_CHUNK
+  const uint32_t dummy_off = (uint32_t)(offsetof(Smem, dummy) - offsetof(Smem, fill)) + 4u * (uint32_t)lane;
   FqOwner<G> own;
   bool flush_pending = false;
   uint32_t next_tile = 0;                                // thread 0: the tile claimed last
@@ -386,6 +405,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
     if (s < NS) { own.qb16[i] = (uint32_t)(__ldg(p.qbase + s) / FQ_CHUNK); own.qcap[i] = __ldg(p.qcap + s); }
   }
   for (int i = tid; i < 48; i += NT) S.raw[FQ_HALO + TB + i] = 0;
+  if (tid < 32) S.dummy[tid] = 0x40000000u;              // far above any bucket capacity
   for (uint32_t i = tid; i < sizeof(S.bucket) / 16; i += NT)
     reinterpret_cast<uint4 *>(S.bucket)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);  // FQ_PAD everywhere
   for (uint32_t u = 2u + (uint32_t)tid; u <= 64u; u += NT) S.recip[u] = 0xFFFFFFFFu / u + 1u;
@@ -464,26 +484,27 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
     FqCensus<G> nxt;
     nxt.mlo = 0; nxt.mhi = 0; nxt.rank0 = 0;
     uint32_t nxt_excl = 0, N_next = 0;
+    // Warp 0 looks back first (every predecessor published a tile ago, so this is one L2 round trip): its latency runs in
+    // parallel with the other warps' copy-out; warp 0's own slices are copied out behind barrier (2) instead.
+    unsigned long long g_tile = 0;
     {
       uint4 nx[VPT];
       if (have_next) fq_census_load<G>(p, tile_next, tid, pol_keep, nx);
-      if (flush_pending) {
-        fq_flush_copy<G>(S, p, own, tid, cap, slo, sb, lomask);
-        flush_pending = false;
-      }
+      if (w == 0) g_tile = fq_lookback(p.tile_state, tile, N, g_in, lane);
+      else if (flush_pending) fq_flush_copy<G>(S, p, own, tid, cap, slo, sb, lomask);
       if (have_next) nxt_excl = fq_census_masks<G>(nx, nxt, wtot_next, lane, w);
     }
     kp_mbar_wait(&S.mbar, it);
 
-    // ---- 2. warp 0 looks back (every predecessor published a tile ago) and leaves the tile's framing constants ---------
+    // ---- 2. the tile's framing constants ---------------------------------------------------------------------------------
     if (w == 0) {
       // the line the tile starts in: where did it begin?
       int head = -17;
       if (lane < 16 && S.raw[15 - lane] == '\n') head = -(lane + 1);
       const unsigned hm = __ballot_sync(0xffffffffu, head != -17);
       if (hm) head = -(__ffs(hm));
-      const unsigned long long g = fq_lookback(p.tile_state, tile, N, g_in, lane);
       if (lane == 0) {
+        const unsigned long long g = g_tile;
         const uint32_t g4 = (uint32_t)g & 3u;
         const uint32_t jr = (1u - g4) & 3u;                      // first line of the tile (tile relative) on phase 1
         S.G_ = g;
@@ -494,7 +515,9 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
         S.ti.jlim = p.max_lines <= g ? 0u : (p.max_lines - g < 0x7fffffffull ? (uint32_t)(p.max_lines - g) : 0x7fffffffu);
       }
     }
-    __syncthreads();  // (2) the framing constants, wtot_next[]; the buckets may be appended to again
+    __syncthreads();  // (2) the framing constants, wtot_next[]
+    if (w == 0 && flush_pending) fq_flush_copy<G>(S, p, own, tid, cap, slo, sb, lomask);  // (barrier (3) comes before any append)
+    flush_pending = false;
     if (have_next) {
       N_next = fq_census_total<G>(wtot_next, nxt_excl, nxt, lane, w);
       if (tid == 0) fq_lookback_publish(p.tile_state, tile_next, N_next, g_in);
@@ -708,7 +731,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
           uint32_t pending = ok;
           if (KT == 12) {
 #pragma unroll
-            for (int jw = 0; jw < FQ_W; jw += FQ_APPEND_GROUP) fq_append4_k12<DS>(S, hi24, lo32, rhi, rlo, jw, ok, pending);
+            for (int jw = 0; jw < FQ_W; jw += FQ_APPEND_GROUP) fq_append4_k12<DS>(S, hi24, lo32, rhi, rlo, jw, ok, pending, dummy_off);
           }
 #pragma unroll
           for (int jw = 0; jw < FQ_W; ++jw) {
