@@ -37,10 +37,10 @@
 
 // tuning switches (defaults = what measured best on a B200; tools/gpu_define_variants.sh rebuilds with -D overrides)
 #ifndef FQ_APPEND_GROUP
-#define FQ_APPEND_GROUP 4   // shared-memory atomics issued back to back per group of windows (1, 2 or 4)
+#define FQ_APPEND_GROUP 1   // shared-memory atomics issued back to back per group of windows (1, 2 or 4)
 #endif
 #ifndef FQ_PADFILL
-#define FQ_PADFILL 1        // 1: windows that are not valid take a bucket position that already reads as padding; 0: they
+#define FQ_PADFILL 0        // 1: windows that are not valid take a bucket position that already reads as padding; 0: they
 #endif                      //    count into per-lane dummy counters instead (one SEL per window, no padding in the queues)
 #ifndef FQ_L2HINTS
 #define FQ_L2HINTS 1        // census loads evict_last, the tile's bulk copy evict_first
