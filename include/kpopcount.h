@@ -90,6 +90,10 @@ int kpc_feed_device(kpc_ctx *ctx, int mate, const void *device_bytes, size_t n, 
  * set the limit to the reported number of complete pairs and feed again */
 int kpc_set_pair_limit(kpc_ctx *ctx, long long n_pairs);
 long long kpc_complete_pairs(const kpc_ctx *ctx);
+/* inputs that cannot be read twice (pipes): with on != 0 paired files are woven pair by pair on the host in EVERY mode
+ * (otherwise only where the reference's order matters: large k, -L, -M spills), so a shorter mate file ends the input
+ * exactly as FASTQ.iter_pe does and KPC_E_PE_MISMATCH never arises.  Call before kpc_begin. */
+int kpc_set_single_pass(kpc_ctx *ctx, int on);
 int kpc_end(kpc_ctx *ctx);
 /* the final KIHF.iter (bin/KPopCount.ml:60) */
 int kpc_finish(kpc_ctx *ctx);

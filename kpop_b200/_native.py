@@ -34,6 +34,7 @@ PROTOTYPES = {
     "kpc_reset_label": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
     "kpc_feed_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
     "kpc_set_pair_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong]),
+    "kpc_set_single_pass": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "kpc_complete_pairs": (ctypes.c_longlong, [ctypes.c_void_p]),
     "kpc_end": (ctypes.c_int, [ctypes.c_void_p]),
     "kpc_finish": (ctypes.c_int, [ctypes.c_void_p]),

@@ -116,6 +116,10 @@ class KMerCounter:
     def set_pair_limit(self, n):
         self._check(self._lib.kpc_set_pair_limit(self._ctx, n))
 
+    def set_single_pass(self, on=True):
+        """weave paired files on the host in every mode: inputs are read once (pipes), a shorter mate ends the pair."""
+        self._check(self._lib.kpc_set_single_pass(self._ctx, 1 if on else 0))
+
     def complete_pairs(self):
         return self._lib.kpc_complete_pairs(self._ctx)
 

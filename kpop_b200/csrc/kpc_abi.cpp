@@ -150,6 +150,9 @@ int kpc_feed_device(kpc_ctx *ctx, int mate, const void *device_bytes, size_t n, 
 int kpc_set_pair_limit(kpc_ctx *ctx, long long n_pairs) {
   return guarded(ctx, [&](KpcEngine &e) { if (ctx->multi) ctx->multi->set_pair_limit(n_pairs); else e.set_pair_limit(n_pairs); });
 }
+int kpc_set_single_pass(kpc_ctx *ctx, int on) {
+  return guarded(ctx, [&](KpcEngine &e) { if (ctx->multi) ctx->multi->set_single_pass(on != 0); else e.set_single_pass(on != 0); });
+}
 long long kpc_complete_pairs(const kpc_ctx *ctx) {
   if (!ctx || !ctx->engine) return -1;
   return ctx->multi ? ctx->multi->complete_pairs() : ctx->engine->complete_pairs();

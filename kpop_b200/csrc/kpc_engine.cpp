@@ -325,7 +325,10 @@ void KpcEngine::begin(int format) {
   // (Files.ml:222-250, 363-368), and both the dump rule (bin/KPopCount.ml:39) and Hashtbl's order depend on that order.
   // The two byte streams are therefore woven into ONE single-end stream of complete pairs on the host (line splitting
   // with memchr: these are not the throughput paths) and everything downstream sees single-end records.
-  pe_weave_ = format == KPC_FASTQ_PE && mode_ != DENSE;
+  // The dense table does not care about order: there the mates are counted independently and a shorter mate is found at
+  // kpc_end (KPC_E_PE_MISMATCH, the caller runs again with a pair limit) -- unless the caller cannot read its inputs
+  // twice (pipes) and has asked for one pass, which weaves as well.
+  pe_weave_ = format == KPC_FASTQ_PE && (mode_ != DENSE || pe_single_pass_);
   if (pe_weave_) {
     format = KPC_FASTQ_SE;
     for (int m = 0; m < 2; ++m) { pe_q_[m].clear(); pe_scan_[m] = 0; pe_rec_end_[m] = 0; pe_lines_[m] = 0; pe_eof_[m] = false; }
@@ -509,6 +512,7 @@ void KpcEngine::pe_pump(bool finishing) {
     if (used[m]) {
       pe_q_[m].erase(pe_q_[m].begin(), pe_q_[m].begin() + used[m]);
       pe_scan_[m] -= used[m];
+      if (pe_rec_end_[m]) pe_rec_end_[m] -= used[m];  // a record of this mate that is still waiting for its partner
     }
   }
   // a mate that has ended with no complete record left: iteration stops (a record of the other mate that was already

@@ -43,6 +43,7 @@ class KpcEngine {
   void feed(int mate, const uint8_t *bytes, size_t n, bool eof);
   void feed_device(int mate, const uint8_t *dev, size_t n, bool eof);
   void set_pair_limit(long long n) { pair_limit_ = n; }
+  void set_single_pass(bool on) { pe_single_pass_ = on; }
   long long complete_pairs() const { return complete_pairs_; }
   void end();
   void finish();
@@ -122,6 +123,7 @@ class KpcEngine {
   // --- paired-end input of hash-table / -L runs: the two mate streams are woven into one, pair by pair, on the host ---
   void pe_enqueue(int mate, const uint8_t *bytes, size_t n, bool eof);
   void pe_pump(bool finishing);
+  bool pe_single_pass_ = false;      // weave paired files on the dense path too (inputs that cannot be read twice)
   bool pe_weave_ = false;            // the current input is a woven pair of files (the engine sees single-end records)
   std::vector<uint8_t> pe_q_[2];     // bytes of each mate not yet woven
   size_t pe_scan_[2] = {0, 0};       // how far each queue has been searched for line feeds

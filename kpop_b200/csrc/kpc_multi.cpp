@@ -77,7 +77,9 @@ void KpcMulti::begin(int format) {
   if (reduced_) throw KpcError(KPC_E_STATE, "kpc_begin after kpc_finish (call kpc_reset first)");
   format_ = format;
   // what shards: FASTQ into the dense table.  Everything else is the first device's business alone.
-  shard_ = eng_.size() > 1 && format != KPC_FASTA && eng_[0]->mode() == KpcEngine::DENSE;
+  // (paired files in one pass are woven on the host, pair by pair: one stream, one device)
+  shard_ = eng_.size() > 1 && format != KPC_FASTA && eng_[0]->mode() == KpcEngine::DENSE &&
+           !(format == KPC_FASTQ_PE && single_pass_);
   in_input_ = true;
   if (!shard_) { rt_set_device(eng_[0]->device()); eng_[0]->begin(format); return; }
   for (size_t i = 0; i < eng_.size(); ++i) { rt_set_device(eng_[i]->device()); eng_[i]->shard_begin(format, i == 0); }

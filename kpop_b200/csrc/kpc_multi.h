@@ -66,8 +66,10 @@ class KpcMulti {
   bool staging_busy_[kSlots] = {false, false, false, false};
   long long pair_limit_ = -1;
   long long complete_pairs_ = -1;
+  bool single_pass_ = false;
 
  public:
   void set_pair_limit(long long n) { pair_limit_ = n; for (auto &e : eng_) e->set_pair_limit(n); }
+  void set_single_pass(bool on) { single_pass_ = on; for (auto &e : eng_) e->set_single_pass(on); }
   long long complete_pairs() const { return shard_ || complete_pairs_ >= 0 ? complete_pairs_ : eng_[0]->complete_pairs(); }
 };

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <fcntl.h>
 #include <string>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <vector>
 
@@ -185,8 +186,8 @@ int feed_files(kpc_ctx *ctx, const Input &in, std::string &err) {
 
 // one complete run; limits[j] < 0: no pair limit on input j.  Returns a KPC_* code; on KPC_E_PE_MISMATCH
 // *bad_input / *pairs say which input stopped and how many complete pairs it holds
-int run(const Params &P, Output &out, const std::vector<long long> &limits, size_t *bad_input, long long *pairs,
-        std::string &err, bool &ctx_failed_early) {
+int run(const Params &P, Output &out, const std::vector<long long> &limits, bool single_pass, size_t *bad_input,
+        long long *pairs, std::string &err, bool &ctx_failed_early) {
   kpc_ctx *ctx = nullptr;
   // which GPUs: KPC_DEVICES=0,1,... (several devices share the FASTQ inputs of a dense-table run), or KPC_DEVICE=n.
   // The argv surface stays the reference's (it keeps -t / --threads reserved but commented out, bin/KPopCount.ml:93,187-194).
@@ -220,6 +221,7 @@ int run(const Params &P, Output &out, const std::vector<long long> &limits, size
     }
   }
   kpc_set_sink(ctx, Output::sink, &out);
+  kpc_set_single_pass(ctx, single_pass ? 1 : 0);
   size_t j = 0;
   for (; j < P.inputs.size(); ++j) {
     kpc_set_pair_limit(ctx, limits[j]);
@@ -296,14 +298,24 @@ int real_main(int argc, char **argv) {
   for (const Input &in : P.inputs) has_pairs |= in.format == KPC_FASTQ_PE;
   Output out;
   std::string captured, err;
-  if (has_pairs) out.capture = &captured;  // a mate file may turn out shorter: text is released at the end
+  // Regular files are counted mate by mate at full speed and, should a mate file turn out shorter, once more with a pair
+  // limit (the text is held back until then).  Pipes and devices can only be read once: pairs are woven on the host.
+  bool single_pass = false;
+  if (has_pairs)
+    for (const Input &in : P.inputs)
+      for (const std::string *name : {&in.file1, &in.file2}) {
+        struct stat sb;
+        if (!name->empty() && stat(name->c_str(), &sb) == 0 && !S_ISREG(sb.st_mode)) single_pass = true;
+      }
+  if (single_pass) has_pairs = false;  // nothing to hold back or to repeat
+  if (has_pairs) out.capture = &captured;
   std::vector<long long> limits(P.inputs.size(), -1);
   bool early = false;
   int rc;
   for (;;) {
     long long pairs = -1;
     size_t bad = 0;
-    rc = run(P, out, limits, &bad, &pairs, err, early);
+    rc = run(P, out, limits, single_pass, &bad, &pairs, err, early);
     if (rc != KPC_E_PE_MISMATCH || limits[bad] >= 0) break;
     // FASTQ.iter_pe stops at the end of the shorter file (Files.ml:228-247): count again with that many pairs
     limits[bad] = pairs;

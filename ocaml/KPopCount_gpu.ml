@@ -32,44 +32,57 @@ module KMerCounter :
       let n_slots = Kpc_gpu.staging_slots ctx and slot = ref 0 and reads_bytes = ref 0 in
       (* Raw bytes, no input_line, no linter: both happen on the device.
          Works on pipes (/dev/stdin) as the reference does: nothing is seeked or mapped *)
-      let stream mate path =
+      let scratch = Bytes.create 65536 in
+      (* one staging buffer's worth of [ic] to the device; true at end of file *)
+      let feed_some mate ic =
+        let buf = Kpc_gpu.staging ctx !slot in
+        let cap = Bigarray.Array1.dim buf in
+        (* Fill the pinned buffer (Unix.read_bigarray needs OCaml >= 5.2; this works from 4.12 on) *)
+        let filled = ref 0 and eof = ref false in
+        while not !eof && !filled < cap do
+          let want = min (Bytes.length scratch) (cap - !filled) in
+          let n = Unix.read ic scratch 0 want in
+          if n = 0 then
+            eof := true
+          else begin
+            for i = 0 to n - 1 do
+              Bigarray.Array1.unsafe_set buf (!filled + i) (Bytes.unsafe_get scratch i)
+            done;
+            filled := !filled + n
+          end
+        done;
+        Kpc_gpu.feed ctx ~mate buf ~len:!filled ~eof:!eof;
+        reads_bytes := !reads_bytes + !filled;
+        if verbose then
+          Printf.eprintf "%s\r(%s): Streamed %d bytes%!" String.TermIO.clear __FUNCTION__ !reads_bytes;
+        slot := (!slot + 1) mod n_slots;
+        !eof in
+      let stream path =
         let ic = Unix.openfile path [ Unix.O_RDONLY ] 0 in
-        let scratch = Bytes.create 65536 in
-        let rec go () =
-          let buf = Kpc_gpu.staging ctx !slot in
-          let cap = Bigarray.Array1.dim buf in
-          (* Fill the pinned buffer (Unix.read_bigarray needs OCaml >= 5.2; this works from 4.12 on) *)
-          let filled = ref 0 and eof = ref false in
-          while not !eof && !filled < cap do
-            let want = min (Bytes.length scratch) (cap - !filled) in
-            let n = Unix.read ic scratch 0 want in
-            if n = 0 then
-              eof := true
-            else begin
-              for i = 0 to n - 1 do
-                Bigarray.Array1.unsafe_set buf (!filled + i) (Bytes.unsafe_get scratch i)
-              done;
-              filled := !filled + n
-            end
-          done;
-          Kpc_gpu.feed ctx ~mate buf ~len:!filled ~eof:!eof;
-          reads_bytes := !reads_bytes + !filled;
-          if verbose then
-            Printf.eprintf "%s\r(%s): Streamed %d bytes%!" String.TermIO.clear __FUNCTION__ !reads_bytes;
-          slot := (!slot + 1) mod n_slots;
-          if not !eof then
-            go () in
-        go ();
-        Unix.close ic in
+        while not (feed_some 0 ic) do () done;
+        Unix.close ic
+      (* the two files of a pair advance together, one buffer each in turn, as FASTQ.iter_pe reads them *)
+      and stream_pair path1 path2 =
+        let ic1 = Unix.openfile path1 [ Unix.O_RDONLY ] 0 in
+        let ic2 = Unix.openfile path2 [ Unix.O_RDONLY ] 0 in
+        let eof1 = ref false and eof2 = ref false in
+        while not (!eof1 && !eof2) do
+          if not !eof1 then eof1 := feed_some 0 ic1;
+          if not !eof2 then eof2 := feed_some 1 ic2
+        done;
+        Unix.close ic1;
+        Unix.close ic2 in
+      (* inputs are read once, like the reference does: a shorter mate file ends its pair of files (Files.ml:228-247) *)
+      Kpc_gpu.set_single_pass ctx true;
       List.iter
         (function
           | Files.Type.FASTA file ->
-            Kpc_gpu.begin_ ctx Kpc_gpu.FASTA; stream 0 file; Kpc_gpu.end_ ctx
+            Kpc_gpu.begin_ ctx Kpc_gpu.FASTA; stream file; Kpc_gpu.end_ ctx
           | SingleEndFASTQ file ->
-            Kpc_gpu.begin_ ctx Kpc_gpu.FASTQ_SE; stream 0 file; Kpc_gpu.end_ ctx
+            Kpc_gpu.begin_ ctx Kpc_gpu.FASTQ_SE; stream file; Kpc_gpu.end_ ctx
           | PairedEndFASTQ (file1, file2) ->
             (* FASTQ.iter_pe alternates the mates pair by pair (Files.ml:222-250); the library re-creates that order *)
-            Kpc_gpu.begin_ ctx Kpc_gpu.FASTQ_PE; stream 0 file1; stream 1 file2; Kpc_gpu.end_ ctx
+            Kpc_gpu.begin_ ctx Kpc_gpu.FASTQ_PE; stream_pair file1 file2; Kpc_gpu.end_ ctx
           | InterleavedFASTQ _ | Tabular _ ->
             assert false) (* not reachable from KPopCount's argv, bin/KPopCount.ml:140,147,157 *)
         inputs;

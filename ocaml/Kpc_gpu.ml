@@ -42,6 +42,8 @@ external finish : ctx -> unit = "kpc_ml_finish"
 (* FASTQ.iter_pe stops at the shorter file (Files.ml:228-247) *)
 external set_pair_limit : ctx -> int -> unit = "kpc_ml_set_pair_limit"
 external complete_pairs : ctx -> int = "kpc_ml_complete_pairs"
+(* one pass over paired files in every mode (the reference reads its inputs once, and they may be pipes) *)
+external set_single_pass : ctx -> bool -> unit = "kpc_ml_set_single_pass"
 external kmers_counted : ctx -> int = "kpc_ml_kmers_counted"
 external reset : ctx -> unit = "kpc_ml_reset"
 external backend : unit -> string = "kpc_ml_backend"

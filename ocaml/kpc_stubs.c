@@ -152,6 +152,12 @@ value kpc_ml_set_pair_limit(value c, value n) {
   CAMLreturn(Val_unit);
 }
 
+value kpc_ml_set_single_pass(value c, value on) {
+  CAMLparam2(c, on);
+  check(Ctx_val(c), kpc_set_single_pass(Ctx_val(c), Bool_val(on)));
+  CAMLreturn(Val_unit);
+}
+
 value kpc_ml_complete_pairs(value c) {
   CAMLparam1(c);
   CAMLreturn(Val_long(kpc_complete_pairs(Ctx_val(c))));

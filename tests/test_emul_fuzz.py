@@ -1,6 +1,7 @@
 """Seeded adversarial inputs through the emulated product path, byte-compared with the oracle (stdout + exit code)."""
 import os
 import random
+import subprocess
 
 import pytest
 
@@ -60,7 +61,20 @@ def test_emul_fuzz_vs_oracle(emul_bin, oracle_bin, tmp_path, seed):
             env["KPC_DEVICES"] = rng.choice(["0,1", "0,1,2"])
             if fmt != "fasta":
                 env["KPC_CHUNK_BYTES"] = str(max(chunk, 8192))
-        rc_e, out_e, err_e = run_cli(emul_bin, argv, env=env)
+        argv_e, writers = argv, []
+        if fmt == "pe" and rng.random() < 0.4:  # the same files through FIFOs: one pass, pairs woven on the host
+            argv_e = list(argv)
+            for i, a in enumerate(argv):
+                if i >= 1 and argv[i - 1] == "-p" or i >= 2 and argv[i - 2] == "-p":
+                    fifo = a + ".fifo"
+                    os.mkfifo(fifo)
+                    writers.append(subprocess.Popen(["sh", "-c", f"exec cat '{a}' > '{fifo}'"], stderr=subprocess.DEVNULL))
+                    argv_e[i] = fifo
+        rc_e, out_e, err_e = run_cli(emul_bin, argv_e, env=env)
+        for w in writers:  # a run that failed early never opened the later FIFOs
+            if w.poll() is None:
+                w.kill()
+            w.wait()
         if rc_e == 2 and b"code -9" in err_e:  # KPC_E_UNSUPPORTED: refused explicitly, never a wrong answer
             refused.append((idx, err_e.decode(errors="replace").strip()[-160:]))
             continue

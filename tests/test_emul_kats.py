@@ -95,3 +95,38 @@ def test_emul_cli_output_prefix_and_pipes(emul_bin, oracle_bin, tmp_path):
         rc_o, out_o, _ = run_cli(oracle_bin, argv + ["-f", str(fa)])
         rc_e, out_e, err_e = run_cli(emul_bin, argv + ["-f", "/dev/stdin"], stdin=fa.read_bytes(), env=env)
         assert (rc_e, out_e) == (rc_o, out_o), err_e
+
+
+def _unequal_mates(seed, n1, n2):
+    import random
+    rng = random.Random(seed)
+    def mate(n, tag, lo, hi):
+        out = []
+        for i in range(n):
+            ln = rng.randint(lo, hi)
+            out.append(b"@r%d/%d\n%s\n+\n%s\n" % (i, tag, bytes(rng.choices(b"ACGTN", weights=[9, 9, 9, 9, 1], k=ln)), b"I" * ln))
+        return b"".join(out)
+    return mate(n1, 1, 20, 60), mate(n2, 2, 10, 50)
+
+
+@pytest.mark.parametrize("n1,n2", [(40, 25), (25, 40), (30, 30), (0, 5)])
+def test_emul_cli_paired_fifos_one_pass(emul_bin, oracle_bin, tmp_path, n1, n2):
+    """Paired-end input from two FIFOs with UNEQUAL numbers of records: FASTQ.iter_pe stops at the shorter file
+    (Files.ml:228-247) and a pipe cannot be read again, so the CLI asks the library for one pass (kpc_set_single_pass);
+    dense table (k = 5), hash table (k = 13) and -L."""
+    m1, m2 = _unequal_mates(n1 * 100 + n2, n1, n2)
+    f1, f2 = tmp_path / "m1.fq", tmp_path / "m2.fq"
+    f1.write_bytes(m1); f2.write_bytes(m2)
+    p1, p2 = str(tmp_path / "p1"), str(tmp_path / "p2")
+    os.mkfifo(p1); os.mkfifo(p2)
+    env = emul_env("8x4", "97")
+    for argv in (["-k", "5", "-l", "x"], ["-k", "13", "-l", "x"], ["-k", "4", "-L"]):
+        rc_o, out_o, _ = run_cli(oracle_bin, argv + ["-p", str(f1), str(f2)])
+        # regular files: the two-pass route
+        rc_f, out_f, err_f = run_cli(emul_bin, argv + ["-p", str(f1), str(f2)], env=env)
+        assert (rc_f, out_f) == (rc_o, out_o), err_f
+        writers = [subprocess.Popen(["sh", "-c", f"cat {f1} > {p1}"]), subprocess.Popen(["sh", "-c", f"cat {f2} > {p2}"])]
+        rc_e, out_e, err_e = run_cli(emul_bin, argv + ["-p", p1, p2], env=env)
+        for w in writers:
+            w.wait()
+        assert (rc_e, out_e) == (rc_o, out_o), err_e
