@@ -33,10 +33,20 @@ extern __shared__ __align__(16) uint8_t fq_smem_raw[];
 
 namespace {
 
-typedef FqGeom<512, 4> FqProd;  // 512 threads x 64 bytes: 32 KiB tiles, two CTAs per SM
+// production geometry (tools/gpu_define_variants.sh rebuilds with other values to measure them)
+#ifndef FQ_PROD_NT
+#define FQ_PROD_NT 512
+#endif
+#ifndef FQ_PROD_VPT
+#define FQ_PROD_VPT 4
+#endif
+#ifndef FQ_PROD_CTAS
+#define FQ_PROD_CTAS 2
+#endif
+typedef FqGeom<FQ_PROD_NT, FQ_PROD_VPT> FqProd;  // 512 threads x 64 bytes: 32 KiB tiles, two CTAs per SM
 
 template <bool DS, int KT>
-__global__ void __launch_bounds__(FqProd::NT, 2) fq_partition_kernel(const KpcFqLaunch p) {
+__global__ void __launch_bounds__(FqProd::NT, FQ_PROD_CTAS) fq_partition_kernel(const KpcFqLaunch p) {
   fq_partition_body<FqProd, DS, KT>(p, fq_smem_raw);
 }
 
@@ -109,6 +119,19 @@ void kpc_fq_partition(const KpcFqLaunch &L, rt_stream s) {
   if (L.k == 12) { if (ds) launch_partition<true, 12>(L, s); else launch_partition<false, 12>(L, s); }
   else { if (ds) launch_partition<true, 0>(L, s); else launch_partition<false, 0>(L, s); }
   if (g_fqt.on) FQ_CUDA_CHECK(cudaEventRecord(fq_timing_event(3 * g_fqt.used + 1), fq_cs(s)));
+#ifdef FQ_PHASE_CLOCKS
+  {  // experiment: print and clear the per-phase cycle counts of this launch
+    unsigned long long h[16], z[16] = {0};
+    FQ_CUDA_CHECK(cudaStreamSynchronize(fq_cs(s)));
+    FQ_CUDA_CHECK(cudaMemcpyFromSymbol(h, g_fq_phase, sizeof h));
+    FQ_CUDA_CHECK(cudaMemcpyToSymbol(g_fq_phase, z, sizeof z));
+    unsigned long long tot = 0;
+    for (int i = 0; i < 15; ++i) tot += h[i];
+    fprintf(stderr, "fq phases (%% of %llu cycles, n = %llu B):", tot, (unsigned long long)L.n);
+    for (int i = 0; i < 15; ++i) fprintf(stderr, " %d:%.1f", i, 100.0 * (double)h[i] / (double)(tot ? tot : 1));
+    fprintf(stderr, "\n");
+  }
+#endif
 }
 
 void kpc_fq_count(const KpcFqLaunch &L, rt_stream s) {

@@ -42,16 +42,30 @@
 #ifndef FQ_PADFILL
 #define FQ_PADFILL 0        // 1: windows that are not valid take a bucket position that already reads as padding; 0: they
 #endif                      //    count into per-lane dummy counters instead (one SEL per window, no padding in the queues)
+#ifndef FQ_STG256
+#define FQ_STG256 1         // bucket chunks leave with one 256-bit store (a whole 32-byte sector) instead of two 128-bit ones
+#endif
 #ifndef FQ_L2HINTS
 #define FQ_L2HINTS 1        // census loads evict_last, the tile's bulk copy evict_first
+#endif
+#ifdef FQ_PHASE_CLOCKS
+__device__ unsigned long long g_fq_phase[16];
+#define FQ_PROBE(i) do { if (tid == 32) { const uint32_t c_ = (uint32_t)clock(); S.dbg[i] += c_ - S.dbg_last; S.dbg_last = c_; } } while (0)
+#else
+#define FQ_PROBE(i) do { } while (0)
 #endif
 constexpr int FQ_W = 16;                          // window-end positions per unit (one thread)
 constexpr int FQ_CTX = 12;                        // context bytes loaded before a unit (>= k - 1)
 constexpr int FQ_HALO = 16;
 constexpr int FQ_BIGROW = 32;                     // rows with more units are expanded by the whole CTA
 constexpr int FQ_MAXSLICES = 512;
-constexpr int FQ_BUCKET_ENTRIES = 24576;          // shared-memory bucket space (u16 entries) shared by all slices
+#ifndef FQ_BUCKET_ENTRIES_V
+#define FQ_BUCKET_ENTRIES_V 24576
+#endif
+constexpr int FQ_BUCKET_ENTRIES = FQ_BUCKET_ENTRIES_V;  // shared-memory bucket space (u16 entries) shared by all slices
 constexpr int FQ_BPAD = 8;                        // entries between two buckets: a stride of cap + 8 entries (28 or 100 words) keeps the owners' 128-bit accesses free of bank conflicts
+constexpr uint32_t FQ_CAP12 = FQ_BUCKET_ENTRIES / FQ_MAXSLICES;   // k = 12 always runs with FQ_MAXSLICES slices: bucket capacity
+constexpr uint32_t FQ_STRIDE12 = (FQ_CAP12 + FQ_BPAD) / 2u;       // and bucket stride in 32-bit words (sl4 = 4 * slice)
 constexpr int FQ_CHUNK = 16;                      // entries per copy-out chunk (32 bytes: one L2 sector)
 constexpr uint16_t FQ_PAD = 0xFFFFu;              // queue entry that pads the last chunk of a CTA (skipped by fq_count)
 constexpr int FQ_PBIAS = 16;                      // row starts are stored + FQ_PBIAS (they begin at -16)
@@ -76,6 +90,9 @@ struct FqSmemT {
   alignas(128) uint8_t raw[FQ_HALO + G::TB + 48];  // raw[16 + i] = tile byte i
   alignas(16) uint16_t bucket[FQ_BUCKET_ENTRIES + FQ_BPAD * FQ_MAXSLICES + 2 * FQ_CHUNK];  // slice s owns [s * (cap + FQ_BPAD), + cap)
   uint32_t fill[FQ_MAXSLICES];                    // entries in the bucket (may run past cap while appending)
+#ifdef FQ_PHASE_CLOCKS
+  unsigned long long dbg[16]; uint32_t dbg_last;  // experiment: cycles per phase, as seen by one thread of warp 1
+#endif
   uint32_t dummy[32];                             // FQ_PADFILL == 0: where the appends of windows that are not valid count
   uint32_t uinfo[G::MAXUNITS];                    // unit -> first window end (low half) | end of its line (high half)
   uint16_t rowS[G::MAXROWS + 2], rowE[G::MAXROWS + 2];  // first byte / line feed of every sequence line, + FQ_PBIAS
@@ -216,7 +233,11 @@ KP_DEV void fq_flush_reserve(FqSmemT<G> &S, const KpcFqLaunch &p, FqOwner<G> &ow
 #endif
       S.fill[s] = f > n ? f - n : 0u;
       own.n[i] = n;
+#ifdef FQ_X_NOATOM
+      if (n) own.g[i] = 0;
+#else
       if (n) own.g[i] = atomicAdd(p.qcursor + s, n);
+#endif
     }
   }
 }
@@ -240,8 +261,16 @@ KP_DEV void fq_flush_copy(FqSmemT<G> &S, const KpcFqLaunch &p, const FqOwner<G> 
     for (uint32_t c = 0; c < my_n; c += FQ_CHUNK) {
       const uint4 v0 = src[c >> 3], v1 = src[(c >> 3) + 1];
       if (my_g + c + FQ_CHUNK <= qc) {
+#ifndef FQ_X_NOSTG
+#if FQ_STG256
+        kp_stg_256(dst + (c >> 3), v0, v1);  // one whole sector per store
+#else
         dst[c >> 3] = v0;
         dst[(c >> 3) + 1] = v1;
+#endif
+#else
+        if (v0.x == 0x12345u && v1.y == 0x54321u) dst[0] = v0;
+#endif
       } else {  // queue full: count in place
         const uint32_t ww[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
@@ -306,8 +335,8 @@ KP_DEV void fq_append4_k12(SmemT &S, uint32_t hi24, uint32_t lo32, uint32_t rhi,
   for (int i = 0; i < GR; ++i) {
     const uint32_t bit = 1u << (FQ_W - 1 - (jw0 + i));
     const uint32_t en = __byte_perm(kk[i], kk[i] >> 1, 0x0071u);  // key[0, 8) | key[17, 24) << 8
-    if ((ok & bit) != 0u && pos[i] < 48u) {
-      *reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(S.bucket) + sl4[i] * 28u + pos[i] * 2u) = (uint16_t)en;
+    if ((ok & bit) != 0u && pos[i] < FQ_CAP12) {
+      *reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(S.bucket) + sl4[i] * FQ_STRIDE12 + pos[i] * 2u) = (uint16_t)en;
       pending ^= bit;
     }
   }
@@ -415,6 +444,9 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
     kp_mbar_init(&S.mbar, 1);
   }
   const unsigned long long g_in = p.carry_in->s1.count;  // lines before the launch
+#ifdef FQ_PHASE_CLOCKS
+  if (tid == 32) { for (int i = 0; i < 16; ++i) S.dbg[i] = 0; S.dbg_last = (uint32_t)clock(); }
+#endif
   __syncthreads();
 
   // one bulk copy per tile: [t0 - 16, t0 + len rounded up to 16); a launch without halo starts a line
@@ -470,6 +502,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
     const bool have_next = tile_next < p.n_tiles;
     uint32_t *wtot_next = S.wtot2 + 32 * (it & 1);
     bool claimed = false, loaded_next = false;
+    FQ_PROBE(0);   // prologue / end of the previous tile
 
     // the tile two grids ahead is pulled into L2 now: its census is taken one tile time from now
     if (tid == 0) {
@@ -490,11 +523,15 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
     {
       uint4 nx[VPT];
       if (have_next) fq_census_load<G>(p, tile_next, tid, pol_keep, nx);
+      FQ_PROBE(13);
       if (w == 0) g_tile = fq_lookback(p.tile_state, tile, N, g_in, lane);
       else if (flush_pending) fq_flush_copy<G>(S, p, own, tid, cap, slo, sb, lomask);
+      FQ_PROBE(14);
       if (have_next) nxt_excl = fq_census_masks<G>(nx, nxt, wtot_next, lane, w);
     }
+    FQ_PROBE(1);   // census of the next tile, look-back or copy-out
     kp_mbar_wait(&S.mbar, it);
+    FQ_PROBE(2);   // wait for the tile's bytes
 
     // ---- 2. the tile's framing constants ---------------------------------------------------------------------------------
     if (w == 0) {
@@ -516,6 +553,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
       }
     }
     __syncthreads();  // (2) the framing constants, wtot_next[]
+    FQ_PROBE(3);
     if (w == 0 && flush_pending) fq_flush_copy<G>(S, p, own, tid, cap, slo, sb, lomask);  // (barrier (3) comes before any append)
     flush_pending = false;
     if (have_next) {
@@ -571,7 +609,9 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
           ++j;
         }
       }
+      FQ_PROBE(4);   // totals, publish, newline walk
       __syncthreads();  // (3) rowS[] / rowE[] of the batch
+      FQ_PROBE(5);
 
       uint32_t nunits = 0, rinfo = 0;
       if ((uint32_t)tid < nrows && NRt) {
@@ -591,6 +631,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
         if (lane == 0 && wsum) { atomicMax(&S.umax, wmax); atomicAdd(&S.usum, wsum); }
       }
       __syncthreads();  // (4)
+      FQ_PROBE(6);   // units per row + barrier
       const uint32_t NR = NRt ? nrows : 0u;
       const uint32_t UPR = S.umax, usum = S.usum;
       const bool uniform = NR * UPR <= usum + (usum >> 2) + 64u;
@@ -647,6 +688,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
       // ---- 5. rounds of NT units ------------------------------------------------------------------------------------------
       for (uint32_t q0 = 0; q0 < U; q0 += NT) {
         const bool last_round = last_batch && q0 + NT >= U;
+        FQ_PROBE(7);   // unit numbering, carry-out / the reserve of the previous round
         // the tile after the next one is claimed late (tiles publish in claim order: an early claim would make every
         // later tile wait for this CTA), but early enough for the atomic to return before the tile ends
         if (last_round && !claimed) {
@@ -711,10 +753,12 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
             rhi = ~(((xh2 >> 1) & 0x55555555u) | ((xh2 & 0x55555555u) << 1)) & 0x00FFFFFFu;
           }
         }
+        FQ_PROBE(8);   // classification
         if (flush_pending) {  // the copy-out reserved after the previous round (its atomic has had time to return)
           fq_flush_copy<G>(S, p, own, tid, cap, slo, sb, lomask);
           flush_pending = false;
         }
+        FQ_PROBE(9);   // copy-out
         __syncthreads();      // (B) the buckets may be appended to again; raw[] has been read for the last time in this round
         if (last_round) {     // nothing reads the tile bytes any more: the next tile may land on them
           if (tid == 0) {
@@ -727,6 +771,7 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
         // window end jw: forward k-mer = bits of hi24:lo32, reverse complement = bits of rhi:rlo, both moved to the top
         // of a 32-bit word (KMers.ml:364-368); min (KMers.ml:388) ignores the bits below because they only matter
         // when the k-mers are equal
+        FQ_PROBE(10);  // barrier (B)
         if (ok) {
           uint32_t pending = ok;
           if (KT == 12) {
@@ -759,7 +804,9 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
             atomicAdd(p.table + (kk >> (32 - 2 * k)), 1u);
           }
         }
+        FQ_PROBE(11);  // appends
         __syncthreads();  // (A) the appends of the round are complete
+        FQ_PROBE(12);  // barrier (A)
         fq_flush_reserve<G>(S, p, own, tid, NS, cap, false);
         flush_pending = true;
       }
@@ -777,6 +824,9 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
     N = N_next;
     __syncthreads();  // tileq[], and rowS[] / rowE[] / the scan scratch are free for the next tile
   }
+#ifdef FQ_PHASE_CLOCKS
+  if (tid == 32) for (int i = 0; i < 16; ++i) atomicAdd(&g_fq_phase[i], S.dbg[i]);
+#endif
   // the CTA leaves: everything still in the buckets goes out, the last chunk of every slice padded
   if (flush_pending) fq_flush_copy<G>(S, p, own, tid, cap, slo, sb, lomask);
   __syncthreads();

@@ -68,6 +68,16 @@ KP_DEV uint4 kp_ldg_stream_hint(const uint8_t *p, unsigned long long policy) {
   return x;
 #endif
 }
+// 256-bit store (one full 32-byte sector per thread; dst 32-byte aligned).  SASS: STG.E.ENL2.256
+KP_DEV void kp_stg_256(void *dst, const uint4 &a, const uint4 &b) {
+#ifdef KPC_SIMT_EMUL
+  memcpy(dst, &a, 16);
+  memcpy((uint8_t *)dst + 16, &b, 16);
+#else
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+#endif
+}
 // L2 eviction policies: a line read with evict_last stays until it is read with evict_first (its last use)
 KP_DEV unsigned long long kp_l2_policy_evict_last() {
 #ifdef KPC_SIMT_EMUL
