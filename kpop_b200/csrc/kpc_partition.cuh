@@ -45,6 +45,9 @@
 #ifndef FQ_STG256
 #define FQ_STG256 1         // bucket chunks leave with one 256-bit store (a whole 32-byte sector) instead of two 128-bit ones
 #endif
+#ifndef FQ_LDG256
+#define FQ_LDG256 1         // census loads of 32 bytes (a whole sector) per thread instead of 16
+#endif
 #ifndef FQ_L2HINTS
 #define FQ_L2HINTS 1        // census loads evict_last, the tile's bulk copy evict_first
 #endif
@@ -372,6 +375,15 @@ template <class G>
 KP_DEV void fq_census_load(const KpcFqLaunch &p, uint32_t tile, int tid, unsigned long long policy, uint4 (&x)[G::VPT]) {
   const uint64_t t0 = (uint64_t)tile * G::TB;
   const int len = (int)((p.n - t0) < (uint64_t)G::TB ? (p.n - t0) : (uint64_t)G::TB);
+#if FQ_LDG256
+  // whole tile, launch on a sector boundary (device inputs only promise 16 bytes): 32 bytes (one sector) per load
+  if (G::VPT >= 2 && len == G::TB && ((unsigned long long)(size_t)p.data & 31ull) == 0ull) {
+#pragma unroll
+    for (int c = 0; c + 1 < G::VPT; c += 2)
+      kp_ldg_stream_hint_256(p.data + t0 + G::SEG * tid + 16 * c, policy, x[c], x[c + 1 < G::VPT ? c + 1 : c]);
+    return;
+  }
+#endif
 #pragma unroll
   for (int c = 0; c < G::VPT; ++c) {
     const int off = G::SEG * tid + 16 * c;

@@ -78,6 +78,23 @@ KP_DEV void kp_stg_256(void *dst, const uint4 &a, const uint4 &b) {
                ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 #endif
 }
+// 256-bit streaming load (32-byte aligned: one whole sector per thread) with an L2 eviction policy.  SASS: LDG.E.NA.ENL2.256
+KP_DEV void kp_ldg_stream_hint_256(const uint8_t *p, unsigned long long policy, uint4 &a, uint4 &b) {
+#ifdef KPC_SIMT_EMUL
+  (void)policy;
+  memcpy(&a, p, 16);
+  memcpy(&b, p + 16, 16);
+#else
+  if (policy)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p), "l"(policy));
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+#endif
+}
 // L2 eviction policies: a line read with evict_last stays until it is read with evict_first (its last use)
 KP_DEV unsigned long long kp_l2_policy_evict_last() {
 #ifdef KPC_SIMT_EMUL
