@@ -371,17 +371,26 @@ struct FqCensus {
   uint32_t mlo, mhi;  // bit b <=> byte SEG * tid + b of the tile is '\n'
   uint32_t rank0;     // line feeds of the tile before this thread's bytes
 };
+// Returns true when x holds the warp-interleaved layout: lane L has bytes [32 L, 32 L + 32) of the warp's first and of
+// its second 1024 bytes (every load instruction covers whole 128-byte lines) instead of its own SEG bytes.
 template <class G>
-KP_DEV void fq_census_load(const KpcFqLaunch &p, uint32_t tile, int tid, unsigned long long policy, uint4 (&x)[G::VPT]) {
+KP_DEV bool fq_census_load(const KpcFqLaunch &p, uint32_t tile, int tid, unsigned long long policy, uint4 (&x)[G::VPT]) {
   const uint64_t t0 = (uint64_t)tile * G::TB;
   const int len = (int)((p.n - t0) < (uint64_t)G::TB ? (p.n - t0) : (uint64_t)G::TB);
 #if FQ_LDG256
   // whole tile, launch on a sector boundary (device inputs only promise 16 bytes): 32 bytes (one sector) per load
   if (G::VPT >= 2 && len == G::TB && ((unsigned long long)(size_t)p.data & 31ull) == 0ull) {
+    if (G::VPT == 4) {
+      const uint8_t *wb = p.data + t0 + (size_t)(G::SEG * 32) * (size_t)(tid >> 5) + 32 * (tid & 31);
+      kp_ldg_stream_hint_256(wb, policy, x[0], x[1]);
+      kp_ldg_stream_hint_256(wb + 1024, policy, x[G::VPT == 4 ? 2 : 0], x[G::VPT == 4 ? 3 : 0]);
+      return true;
+    } else {
 #pragma unroll
-    for (int c = 0; c + 1 < G::VPT; c += 2)
-      kp_ldg_stream_hint_256(p.data + t0 + G::SEG * tid + 16 * c, policy, x[c], x[c + 1 < G::VPT ? c + 1 : c]);
-    return;
+      for (int c = 0; c + 1 < G::VPT; c += 2)
+        kp_ldg_stream_hint_256(p.data + t0 + G::SEG * tid + 16 * c, policy, x[c], x[c + 1 < G::VPT ? c + 1 : c]);
+      return false;
+    }
   }
 #endif
 #pragma unroll
@@ -396,16 +405,26 @@ KP_DEV void fq_census_load(const KpcFqLaunch &p, uint32_t tile, int tid, unsigne
       x[c].w = fq_keep_bytes(x[c].w, len - off - 12);
     }
   }
+  return false;
 }
 // masks + warp scan; lane 31 leaves the warp's total in wtot[w]; returns the inclusive count of the thread
 template <class G>
-KP_DEV uint32_t fq_census_masks(const uint4 (&x)[G::VPT], FqCensus<G> &c, uint32_t *wtot, int lane, int w) {
+KP_DEV uint32_t fq_census_masks(const uint4 (&x)[G::VPT], bool interleaved, FqCensus<G> &c, uint32_t *wtot, int lane, int w) {
   uint32_t m16[G::VPT];
 #pragma unroll
   for (int i = 0; i < G::VPT; ++i) m16[i] = fq_nl_mask16(x[i]);
   c.mlo = m16[0]; c.mhi = 0;
   if (G::VPT >= 2) c.mlo |= m16[G::VPT >= 2 ? 1 : 0] << 16;
   if (G::VPT == 4) c.mhi = m16[G::VPT == 4 ? 2 : 0] | (m16[G::VPT == 4 ? 3 : 0] << 16);
+  if (G::VPT == 4 && interleaved) {
+    // c.mlo / c.mhi are the masks of sector `lane` of the warp's first / second 1024 bytes; this thread's 64 bytes are
+    // sectors 2 lane and 2 lane + 1 of the warp's 2048 bytes
+    const int s0 = (2 * lane) & 31, s1 = (2 * lane + 1) & 31;
+    const uint32_t a0 = __shfl_sync(0xffffffffu, c.mlo, s0), a1 = __shfl_sync(0xffffffffu, c.mhi, s0);
+    const uint32_t b0 = __shfl_sync(0xffffffffu, c.mlo, s1), b1 = __shfl_sync(0xffffffffu, c.mhi, s1);
+    c.mlo = lane < 16 ? a0 : a1;
+    c.mhi = lane < 16 ? b0 : b1;
+  }
   const uint32_t cnt = (uint32_t)__popc(c.mlo) + (uint32_t)__popc(c.mhi);
   const uint32_t inc = fq_warp_incl_scan(cnt, lane);
   if (lane == 31) wtot[w] = inc;
@@ -492,8 +511,8 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
     }
     if (tile0 < p.n_tiles) {
       uint4 x[VPT];
-      fq_census_load<G>(p, tile0, tid, pol_keep, x);
-      excl = fq_census_masks<G>(x, cur, S.wtot, lane, w);
+      const bool il = fq_census_load<G>(p, tile0, tid, pol_keep, x);
+      excl = fq_census_masks<G>(x, il, cur, S.wtot, lane, w);
     }
     if (tid == 0) {
       S.tileq[1] = tile0 < p.n_tiles ? atomicAdd(p.counters, 1u) : 0xffffffffu;
@@ -534,12 +553,13 @@ KP_DEV void fq_partition_body(const KpcFqLaunch &p, uint8_t *smem_raw) {
     unsigned long long g_tile = 0;
     {
       uint4 nx[VPT];
-      if (have_next) fq_census_load<G>(p, tile_next, tid, pol_keep, nx);
+      bool il = false;
+      if (have_next) il = fq_census_load<G>(p, tile_next, tid, pol_keep, nx);
       FQ_PROBE(13);
       if (w == 0) g_tile = fq_lookback(p.tile_state, tile, N, g_in, lane);
       else if (flush_pending) fq_flush_copy<G>(S, p, own, tid, cap, slo, sb, lomask);
       FQ_PROBE(14);
-      if (have_next) nxt_excl = fq_census_masks<G>(nx, nxt, wtot_next, lane, w);
+      if (have_next) nxt_excl = fq_census_masks<G>(nx, il, nxt, wtot_next, lane, w);
     }
     FQ_PROBE(1);   // census of the next tile, look-back or copy-out
     kp_mbar_wait(&S.mbar, it);

@@ -13,7 +13,13 @@ void rt_init(int) {}
 int rt_sm_count() { return 4; }
 void rt_set_device(int) {}
 int rt_current_device() { return 0; }
-void *rt_dmalloc(size_t n) { return calloc(1, n ? n + 64 : 64); }
+// 256-byte aligned like cudaMalloc (the kernels take wider loads on sector-aligned launches)
+void *rt_dmalloc(size_t n) {
+  const size_t sz = ((n ? n + 64 : 64) + 255) & ~(size_t)255;
+  void *p = aligned_alloc(256, sz);
+  if (p) memset(p, 0, sz);
+  return p;
+}
 void rt_dfree(void *p) { free(p); }
 void *rt_hmalloc(size_t n) { return malloc(n ? n : 1); }
 void rt_hfree(void *p) { free(p); }
