@@ -542,6 +542,7 @@ void KpcEngine::submit_host(StreamState &st, int mate, const Piece *pc, int npc,
     for (int j = 0; j < 2; ++j)
       if (pc[i].p == st.hold[j]) { rt_event_record(st.hold_ev[j], copy_); st.hold_busy[j] = true; }
   }
+  rt_memset(slot.buf + off, 0, 16, copy_);  // the kernels read whole 16-byte vectors: the bytes past the end are masked, not undefined
   rt_event ev = rt_event_create();
   rt_event_record(ev, copy_);
   rt_stream_wait(compute_, ev);
