@@ -60,6 +60,9 @@ void kpc_k_hash_extract(const unsigned long long *keys, const unsigned long long
 // ---- sort path (kpc_bucketsort.cuh): a whole large-k sample without a hash table ----
 // exclusive prefix sums of hist[0..nb) into offsets[0..nb]; offsets[nb] = total
 void kpc_k_bucket_offsets(const uint32_t *hist, uint32_t nb, uint32_t *offsets, void *scratch, rt_stream s);
+// scatter pass over staged (key, rank) pairs (KpcBucketCountSink::stage_*): *n pairs, n read on the device
+void kpc_k_bucket_scatter_staged(const unsigned long long *stage_keys, const unsigned long long *stage_ranks,
+                                 const unsigned long long *n, const KpcBucketScatterSink &sink, rt_stream s);
 struct KpcBucketFinalize {
   const uint32_t *offsets;            // nb + 1 entries
   uint32_t nb;

@@ -251,7 +251,27 @@ struct KpcBucketCountSink {
   uint32_t *hist;
   uint64_t bmask;  // B - 1
   int cshift;      // coarse bucket = (key & bmask) >> cshift
-  KPC_HD void emit(uint64_t key, uint64_t /*rank*/, uint64_t /*rec*/) const { kpc_red_add_u32(hist + ((key & bmask) >> cshift), 1u); }
+  // optional staging: the (key, rank) pairs in arrival order, so that the scatter pass is a plain streaming kernel
+  // (kpc_k_bucket_scatter_staged) instead of a second run of the framing machine
+  unsigned long long *stage_keys, *stage_ranks, *stage_n;
+  KPC_HD void emit(uint64_t key, uint64_t rank, uint64_t /*rec*/) const {
+    kpc_red_add_u32(hist + ((key & bmask) >> cshift), 1u);
+    if (stage_keys) {
+#if KPC_ON_DEVICE
+      // one atomic per warp: the lanes that are here together take consecutive places
+      const unsigned m = __activemask();
+      const int leader = __ffs(m) - 1, lane = (int)(threadIdx.x & 31u);
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(stage_n, (unsigned long long)__popc(m));
+      base = __shfl_sync(m, base, leader);
+      const unsigned long long i = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+#else
+      const unsigned long long i = kpc_atomic_add_u64(stage_n, 1ull);
+#endif
+      stage_keys[i] = key;
+      stage_ranks[i] = rank;
+    }
+  }
 };
 struct KpcBucketScatterSink {
   uint32_t *remaining;       // pass 1's counts, counted down to zero here
