@@ -53,6 +53,8 @@ def parse_args():
                          "GPUs (strong scaling); c4: ~5 Mb genomes at k = 30, sharded by sample")
     ap.add_argument("--records-per-gpu", type=int, default=None)
     ap.add_argument("--genomes-per-gpu", type=int, default=16)
+    ap.add_argument("--contexts", type=int, default=2,
+                    help="c4: library contexts per GPU, each fed by its own host thread (samples are independent)")
     ap.add_argument("--cpu-sample-records", type=int, default=1_500_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
