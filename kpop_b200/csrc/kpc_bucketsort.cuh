@@ -1,6 +1,6 @@
 // kpc_bucketsort.cuh -- the second half of the sort path for large-k samples.
 //
-// After the two counting-sort passes of the framing kernel (KpcBucketCountSink / KpcBucketScatterSink, kpc_tile.cuh)
+// After the counting pass of the framing kernel and the streaming scatter (KpcBucketCountSink / KpcBucketScatterSink, kpc_tile.cuh)
 // the (key, rank) pairs of all windows of a sample sit grouped by coarse bucket -- the top bits of (key mod B), B =
 // the bucket count of OCaml's Hashtbl (BiOCamLib/lib/Better.ml:741, KMers.ml:99-113) -- in arbitrary order inside a
 // group.  This file turns every group into what KIHF.iter prints (bin/KPopCount.ml:60):
@@ -52,7 +52,8 @@ KP_DEV void kpc_bucket_finalize_small(const KpcBucketFinalize &F, uint32_t b, ui
   }
   unsigned long long k[KPC_BS_SMALL], r[KPC_BS_SMALL], c[KPC_BS_SMALL];
   for (uint32_t i = 0; i < n; ++i) {  // insertion sort, order 1
-    const unsigned long long ki = F.keys[lo + i], ri = F.ranks[lo + i];
+    const KpcPair pr = F.pairs[lo + i];
+    const unsigned long long ki = pr.key, ri = pr.rank;
     uint32_t j = i;
     while (j > 0 && kpc_bs_less1(ki, ri, k[j - 1], r[j - 1], F.bmask)) { k[j] = k[j - 1]; r[j] = r[j - 1]; --j; }
     k[j] = ki; r[j] = ri;
@@ -107,7 +108,7 @@ KP_DEV void kpc_bucket_finalize_heavy_body(const KpcBucketFinalize &F, uint8_t *
       continue;
     }
     __syncthreads();
-    for (uint32_t i = tid; i < n; i += NT) { S.k[i] = F.keys[lo + i]; S.r[i] = F.ranks[lo + i]; }
+    for (uint32_t i = tid; i < n; i += NT) { const KpcPair pr = F.pairs[lo + i]; S.k[i] = pr.key; S.r[i] = pr.rank; }
     __syncthreads();
     for (uint32_t i = tid; i < n; i += NT) {  // order 1 by ranking
       const unsigned long long ki = S.k[i], ri = S.r[i];

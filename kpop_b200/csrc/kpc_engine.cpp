@@ -1256,13 +1256,13 @@ bool KpcEngine::sort_process(StreamState &st, int mate, const uint8_t *dev, size
   const int cshift = lb - lnb;
   const size_t heavy_cap = 4096;
   // layout: hist[nb] | offsets[nb + 1] | heavy[heavy_cap] | stats[4] | scan scratch | keys[len] | ranks[len] | counts[len]
-  //         | staged keys[len] | staged ranks[len]   (stats[3] counts the staged pairs)
+  //         | pairs[len] (scatter target) | staged pairs[len]   (stats[3] counts the staged pairs)
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t o_hist = 0, o_off = o_hist + al(4 * (size_t)nb), o_heavy = o_off + al(4 * ((size_t)nb + 1)),
                o_stats = o_heavy + al(4 * heavy_cap), o_scan = o_stats + 256,
                o_keys = o_scan + al(kpc_k_scan_scratch_bytes(nb) + 512), o_ranks = o_keys + al(8 * len),
-               o_counts = o_ranks + al(8 * len), o_skeys = o_counts + al(8 * len), o_sranks = o_skeys + al(8 * len),
-               total = o_sranks + al(8 * len);
+               o_counts = o_ranks + al(8 * len), o_pairs = o_counts + al(8 * len), o_stage = o_pairs + al(16 * len),
+               total = o_stage + al(16 * len);
   if (total > sort_buf_cap_) {
     rt_stream_sync(compute_);
     rt_dfree(sort_buf_);
@@ -1279,15 +1279,15 @@ bool KpcEngine::sort_process(StreamState &st, int mate, const uint8_t *dev, size
   // ONE run of the framing machine: bucket sizes + the (key, rank) pairs in arrival order; the scatter streams them
   KpcBucketCountSink bc;
   bc.hist = hist; bc.bmask = buckets_ - 1; bc.cshift = cshift;
-  bc.stage_keys = (unsigned long long *)(B + o_skeys); bc.stage_ranks = (unsigned long long *)(B + o_sranks); bc.stage_n = stats + 3;
+  bc.stage = (KpcPair *)(B + o_stage); bc.stage_n = stats + 3;
   launch_tiles(st, mate, dev, len, true, max_lines, KPC_SINK_BCOUNT, nullptr, nullptr, false, nullptr, 0, &bc, nullptr);
   kpc_k_bucket_offsets(hist, nb, offsets, B + o_scan, compute_);
   launches_ += 4;
   KpcBucketScatterSink bs;
-  bs.remaining = hist; bs.offsets = offsets; bs.keys = skeys_; bs.ranks = sranks_; bs.bmask = buckets_ - 1; bs.cshift = cshift;
-  kpc_k_bucket_scatter_staged(bc.stage_keys, bc.stage_ranks, bc.stage_n, bs, compute_);
+  bs.remaining = hist; bs.offsets = offsets; bs.pairs = (KpcPair *)(B + o_pairs); bs.bmask = buckets_ - 1; bs.cshift = cshift;
+  kpc_k_bucket_scatter_staged(bc.stage, bc.stage_n, bs, compute_);
   KpcBucketFinalize F;
-  F.offsets = offsets; F.nb = nb; F.keys = skeys_; F.ranks = sranks_; F.counts = scounts_; F.bmask = buckets_ - 1;
+  F.offsets = offsets; F.nb = nb; F.pairs = bs.pairs; F.keys = skeys_; F.ranks = sranks_; F.counts = scounts_; F.bmask = buckets_ - 1;
   F.heavy_list = heavy; F.heavy_cap = (uint32_t)heavy_cap; F.stats = stats;
   kpc_k_bucket_finalize(F, compute_);
   launches_ += 2;

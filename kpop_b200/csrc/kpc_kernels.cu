@@ -472,15 +472,17 @@ void kpc_k_bucket_offsets(const uint32_t *hist, uint32_t nb, uint32_t *offsets, 
   bucket_total_kernel<<<1, 1, 0, cs(s)>>>(total, offsets, nb);
   CUDA_CHECK(cudaGetLastError());
 }
-__global__ void __launch_bounds__(256) bucket_scatter_staged_kernel(const unsigned long long *stage_keys, const unsigned long long *stage_ranks,
-                                                                    const unsigned long long *n, const KpcBucketScatterSink sink) {
+__global__ void __launch_bounds__(256) bucket_scatter_staged_kernel(const KpcPair *stage, const unsigned long long *n,
+                                                                    const KpcBucketScatterSink sink) {
   const unsigned long long N = *n, stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
-    sink.emit(stage_keys[i], stage_ranks[i], 0);
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    const KpcPair pr = stage[i];
+    sink.emit(pr.key, pr.rank, 0);
+  }
 }
-void kpc_k_bucket_scatter_staged(const unsigned long long *stage_keys, const unsigned long long *stage_ranks,
-                                 const unsigned long long *n, const KpcBucketScatterSink &sink, rt_stream s) {
-  bucket_scatter_staged_kernel<<<148 * 8, 256, 0, cs(s)>>>(stage_keys, stage_ranks, n, sink);
+void kpc_k_bucket_scatter_staged(const KpcPair *stage, const unsigned long long *n, const KpcBucketScatterSink &sink,
+                                 rt_stream s) {
+  bucket_scatter_staged_kernel<<<148 * 8, 256, 0, cs(s)>>>(stage, n, sink);
   CUDA_CHECK(cudaGetLastError());
 }
 extern __shared__ __align__(16) uint8_t kpc_dyn_smem[];

@@ -61,12 +61,13 @@ void kpc_k_hash_extract(const unsigned long long *keys, const unsigned long long
 // exclusive prefix sums of hist[0..nb) into offsets[0..nb]; offsets[nb] = total
 void kpc_k_bucket_offsets(const uint32_t *hist, uint32_t nb, uint32_t *offsets, void *scratch, rt_stream s);
 // scatter pass over staged (key, rank) pairs (KpcBucketCountSink::stage_*): *n pairs, n read on the device
-void kpc_k_bucket_scatter_staged(const unsigned long long *stage_keys, const unsigned long long *stage_ranks,
-                                 const unsigned long long *n, const KpcBucketScatterSink &sink, rt_stream s);
+void kpc_k_bucket_scatter_staged(const KpcPair *stage, const unsigned long long *n, const KpcBucketScatterSink &sink,
+                                 rt_stream s);
 struct KpcBucketFinalize {
   const uint32_t *offsets;            // nb + 1 entries
   uint32_t nb;
-  unsigned long long *keys, *ranks;   // in: pairs grouped by coarse bucket; out: entries
+  const KpcPair *pairs;               // in: (key, rank) pairs grouped by coarse bucket
+  unsigned long long *keys, *ranks;   // out: entries
   unsigned long long *counts;         // out
   unsigned long long bmask;           // B - 1
   uint32_t *heavy_list;               // groups left to the CTA-wide kernel

@@ -247,16 +247,19 @@ struct KpcTupleSink {
 // table.  Pass 1 counts the windows of every coarse bucket -- the top bits of (key mod B), B = OCaml's bucket count --,
 // pass 2 drops every window into its bucket's range of one (key, rank) array (the order inside a range is arbitrary:
 // kpc_bucketsort.cuh sorts, merges duplicates and restores Hashtbl.iter order range by range).
+// one k-mer window of the sort path: its key and its rank (position in input order); one 16-byte store / load
+struct alignas(16) KpcPair { unsigned long long key, rank; };
 struct KpcBucketCountSink {
   uint32_t *hist;
   uint64_t bmask;  // B - 1
   int cshift;      // coarse bucket = (key & bmask) >> cshift
   // optional staging: the (key, rank) pairs in arrival order, so that the scatter pass is a plain streaming kernel
   // (kpc_k_bucket_scatter_staged) instead of a second run of the framing machine
-  unsigned long long *stage_keys, *stage_ranks, *stage_n;
+  KpcPair *stage;
+  unsigned long long *stage_n;
   KPC_HD void emit(uint64_t key, uint64_t rank, uint64_t /*rec*/) const {
     kpc_red_add_u32(hist + ((key & bmask) >> cshift), 1u);
-    if (stage_keys) {
+    if (stage) {
 #if KPC_ON_DEVICE
       // one atomic per warp: the lanes that are here together take consecutive places
       const unsigned m = __activemask();
@@ -268,23 +271,23 @@ struct KpcBucketCountSink {
 #else
       const unsigned long long i = kpc_atomic_add_u64(stage_n, 1ull);
 #endif
-      stage_keys[i] = key;
-      stage_ranks[i] = rank;
+      KpcPair pr; pr.key = key; pr.rank = rank;
+      stage[i] = pr;
     }
   }
 };
 struct KpcBucketScatterSink {
   uint32_t *remaining;       // pass 1's counts, counted down to zero here
   const uint32_t *offsets;   // exclusive prefix sums of the counts
-  unsigned long long *keys, *ranks;
+  KpcPair *pairs;
   uint64_t bmask;
   int cshift;
   KPC_HD void emit(uint64_t key, uint64_t rank, uint64_t /*rec*/) const {
     const uint64_t b = (key & bmask) >> cshift;
     const uint32_t left = kpc_atomic_add_u32(remaining + b, 0xFFFFFFFFu);  // -1
     const uint64_t pos = (uint64_t)offsets[b] + left - 1u;
-    keys[pos] = key;
-    ranks[pos] = rank;
+    KpcPair pr; pr.key = key; pr.rank = rank;
+    pairs[pos] = pr;
   }
 };
 

@@ -122,9 +122,8 @@ void kpc_k_format(const unsigned long long *keys, const unsigned long long *coun
     if (counts[i]) o += (size_t)sprintf(out + o, "%0*llx\t%llu\n", hex_width, keys[i], counts[i]);
   *out_len = o;
 }
-void kpc_k_bucket_scatter_staged(const unsigned long long *stage_keys, const unsigned long long *stage_ranks,
-                                 const unsigned long long *n, const KpcBucketScatterSink &sink, rt_stream) {
-  for (unsigned long long i = 0; i < *n; ++i) sink.emit(stage_keys[i], stage_ranks[i], 0);
+void kpc_k_bucket_scatter_staged(const KpcPair *stage, const unsigned long long *n, const KpcBucketScatterSink &sink, rt_stream) {
+  for (unsigned long long i = 0; i < *n; ++i) sink.emit(stage[i].key, stage[i].rank, 0);
 }
 void kpc_k_bucket_offsets(const uint32_t *hist, uint32_t nb, uint32_t *offsets, void *, rt_stream) {
   uint32_t acc = 0;
