@@ -299,8 +299,15 @@ struct KpcTileShared {
   static const int NT = NT_, SEG = SEG_, T = NT_ * SEG_;
   static const int GS = NT_ < 32 ? NT_ : 32;  // scan group = one warp on the device
   static const int NG = NT_ / GS;
-  alignas(16) uint8_t raw[16 + T + 16];  // raw[16+i] = tile byte i, raw[15] = byte before, raw[16+len] = byte after
-  alignas(16) uint8_t cls[T];
+  // Tile byte i lives at raw[px(i)]: 4 bytes of padding after every SEG bytes, so that the threads of a warp -- each
+  // walking its own SEG consecutive bytes -- hit different banks (with SEG = 64 and no padding thread t reads word
+  // 16 t + c: two banks for the whole warp, a 16-way conflict on every byte access).  raw[px(len)] = byte after the
+  // tile, `before` = byte before it; cls[] (one class code per byte) uses the same layout.
+  static const int TP = T + (T / SEG_) * 4 + 8;
+  KPC_HD static int px(int i) { return i + (i / SEG_) * 4; }
+  alignas(16) uint8_t raw[TP];
+  alignas(16) uint8_t cls[TP];
+  uint8_t before;
   KpcS1 pre[NT];     // per-thread census, then exclusive prefix inside its group
   KpcS1 gpre[NG];    // group totals, then exclusive prefix over groups
   KpcS1 tile_in;     // absolute state at the tile start
@@ -347,11 +354,19 @@ struct KpcTileMachine {
       asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                    : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
                    : "l"(src + 16 * v));
-      *reinterpret_cast<uint4 *>(sh.raw + 16 + 16 * v) = x;
+      if (SEG % 4 == 0) {  // a 4-byte word never straddles a padding gap
+        *reinterpret_cast<uint32_t *>(sh.raw + Shared::px(16 * v)) = x.x;
+        *reinterpret_cast<uint32_t *>(sh.raw + Shared::px(16 * v + 4)) = x.y;
+        *reinterpret_cast<uint32_t *>(sh.raw + Shared::px(16 * v + 8)) = x.z;
+        *reinterpret_cast<uint32_t *>(sh.raw + Shared::px(16 * v + 12)) = x.w;
+      } else {
+        const uint32_t wds[4] = {x.x, x.y, x.z, x.w};
+        for (int j = 0; j < 16; ++j) sh.raw[Shared::px(16 * v + j)] = (uint8_t)(wds[j >> 2] >> (8 * (j & 3)));
+      }
 #else
       for (int j = 0; j < 16; ++j) {
         uint64_t q = t0 + 16 * (uint64_t)v + j;
-        sh.raw[16 + 16 * v + j] = q < p.n ? src[16 * v + j] : (uint8_t)'\n';
+        sh.raw[Shared::px(16 * v + j)] = q < p.n ? src[16 * v + j] : (uint8_t)'\n';
       }
 #endif
     }
@@ -360,7 +375,7 @@ struct KpcTileMachine {
       uint8_t before;
       if (t0 > 0) before = p.data[t0 - 1];
       else before = (uint8_t)kpc_ld_cg_u32(&p.carry_in->last_byte);
-      sh.raw[15] = before;
+      sh.before = before;
     }
     if (nvec > 0 && tid == (nvec - 1) % NT) {
       // the byte after the tile (look-ahead for "is the record name empty"), written by the thread that
@@ -368,10 +383,12 @@ struct KpcTileMachine {
       // true end of file, or a cut the host made just after a line feed (never after a '>' that starts a
       // line, see kpc_engine.cpp).  Bytes past the tile inside the last vector are never interpreted.
       uint64_t q = t0 + sh.len;
-      sh.raw[16 + sh.len] = q >= p.n ? (uint8_t)'\n' : p.data[q];
+      sh.raw[Shared::px((int)sh.len)] = q >= p.n ? (uint8_t)'\n' : p.data[q];
     }
   }
 
+  // tile byte i, -1 <= i <= len
+  KPC_HD static uint8_t rawb(const Shared &sh, int i) { return i < 0 ? sh.before : sh.raw[Shared::px(i)]; }
   KPC_HD static int seg_lo(const Shared &sh, int tid) { int a = tid * SEG; return a < (int)sh.len ? a : (int)sh.len; }
   KPC_HD static int seg_hi(const Shared &sh, int tid) { int a = tid * SEG + SEG; return a < (int)sh.len ? a : (int)sh.len; }
 
@@ -380,14 +397,14 @@ struct KpcTileMachine {
     const int lo = seg_lo(sh, tid), hi = seg_hi(sh, tid);
     const uint64_t abs0 = p.abs_base + tile_start(sh);
     KpcS1 s = kpc_s1_identity();
-    uint8_t prev = sh.raw[16 + lo - 1];
+    uint8_t prev = rawb(sh, lo - 1);
     for (int i = lo; i < hi; ++i) {
-      uint8_t b = sh.raw[16 + i];
+      uint8_t b = sh.raw[Shared::px(i)];
       if (b == '\n') {
         s.last_nl = abs0 + i + 1;
         if (FMT == KPC_FMT_FASTQ) s.count++;
       } else if (FMT == KPC_FMT_FASTA && b == '>' && prev == '\n') {
-        uint64_t named = sh.raw[16 + i + 1] != '\n' ? 1u : 0u;
+        uint64_t named = sh.raw[Shared::px(i + 1)] != '\n' ? 1u : 0u;
         s.last_hdr = ((abs0 + i + 1) << 1) | named;
         s.count++;
       }
@@ -459,11 +476,11 @@ struct KpcTileMachine {
     if (lo >= hi) return;
     const uint64_t abs0 = p.abs_base + tile_start(sh);
     KpcS1 st = kpc_s1_combine(sh.tile_in, kpc_s1_combine(sh.gpre[tid / Shared::GS], sh.pre[tid]));
-    uint8_t prev = sh.raw[16 + lo - 1];
+    uint8_t prev = rawb(sh, lo - 1);
     if (FMT == KPC_FMT_FASTQ) {
       uint64_t line = st.count;
       for (int i = lo; i < hi; ++i) {
-        const uint8_t b = sh.raw[16 + i];
+        const uint8_t b = sh.raw[Shared::px(i)];
         const bool at_start = prev == '\n';
         const uint32_t ph = (uint32_t)line & 3u;
         const bool live = line < p.max_lines;
@@ -486,13 +503,13 @@ struct KpcTileMachine {
         } else if (ph == 1 && live) {
           c = classify_symbol(b);
         }
-        sh.cls[i] = c;
+        sh.cls[Shared::px(i)] = c;
         prev = b;
       }
     } else {
       uint64_t last_nl = st.last_nl, last_hdr = st.last_hdr, nrec = st.count;
       for (int i = lo; i < hi; ++i) {
-        const uint8_t b = sh.raw[16 + i];
+        const uint8_t b = sh.raw[Shared::px(i)];
         uint8_t c;
         if (b == '\n') {
           c = KPC_CLS_SKIP;
@@ -502,7 +519,7 @@ struct KpcTileMachine {
           }
           last_nl = abs0 + i + 1;
         } else if (b == '>' && prev == '\n') {
-          uint64_t named = sh.raw[16 + i + 1] != '\n' ? 1u : 0u;
+          uint64_t named = sh.raw[Shared::px(i + 1)] != '\n' ? 1u : 0u;
           last_hdr = ((abs0 + i + 1) << 1) | named;
           c = KPC_CLS_BREAK;
           if (p.probe_pos && abs0 + i >= p.probe_from) kpc_atomic_min_u64(p.probe_pos, abs0 + i);
@@ -518,7 +535,7 @@ struct KpcTileMachine {
         } else {
           c = classify_symbol(b);
         }
-        sh.cls[i] = c;
+        sh.cls[Shared::px(i)] = c;
         prev = b;
       }
     }
@@ -530,7 +547,7 @@ struct KpcTileMachine {
     KpcKCarry c = kpc_kc_identity();
     if (p.k == 1) c.closed = 1;  // windows of one symbol never cross a boundary
     for (int i = (int)sh.len - 1; i >= 0 && !c.closed; --i) {
-      uint8_t x = sh.cls[i];
+      uint8_t x = sh.cls[Shared::px(i)];
       if (x == KPC_CLS_SKIP) continue;
       if (x == KPC_CLS_BREAK) { c.closed = 1; break; }
       c.syms |= (uint64_t)x << (c.n * SB);
@@ -581,7 +598,7 @@ struct KpcTileMachine {
     // warm-up: walk back over the class codes (tile start acts as a break: older symbols are the fix-up's)
     Roll w; w.f = 0; w.r = 0; w.len = 0;
     for (int i = lo - 1; i >= 0 && w.len < (uint32_t)(k - 1); --i) {
-      uint8_t x = sh.cls[i];
+      uint8_t x = sh.cls[Shared::px(i)];
       if (x == KPC_CLS_SKIP) continue;
       if (x == KPC_CLS_BREAK) break;
       w.f |= (uint64_t)x << (w.len * SB);
@@ -589,10 +606,10 @@ struct KpcTileMachine {
       w.len++;
     }
     for (int i = lo; i < hi; ++i) {
-      uint8_t x = sh.cls[i];
+      uint8_t x = sh.cls[Shared::px(i)];
       // keep the record counter in step with classify(): '\n' (FASTQ) / header start (FASTA)
-      if (FMT == KPC_FMT_FASTQ) { if (sh.raw[16 + i] == '\n') { ++cnt; line_start = abs0 + i + 1; } }
-      else if (x == KPC_CLS_BREAK && sh.raw[16 + i] == '>' && sh.raw[16 + i - 1] == '\n') ++cnt;
+      if (FMT == KPC_FMT_FASTQ) { if (sh.raw[Shared::px(i)] == '\n') { ++cnt; line_start = abs0 + i + 1; } }
+      else if (x == KPC_CLS_BREAK && sh.raw[Shared::px(i)] == '>' && rawb(sh, i - 1) == '\n') ++cnt;
       if (x == KPC_CLS_SKIP) continue;
       if (x == KPC_CLS_BREAK) { w.len = 0; continue; }
       push(w, x, k, mask_f);
@@ -643,7 +660,7 @@ struct KpcTileMachine {
     kpc_flag_release(&d->flag2, (p.epoch << 2) | KPC_ST_INC);
     if (sh.tile == p.n_tiles - 1) {
       p.carry_out->kc.syms = inc.syms; p.carry_out->kc.n = inc.n; p.carry_out->kc.closed = 1;
-      p.carry_out->last_byte = sh.raw[16 + sh.len - 1];
+      p.carry_out->last_byte = rawb(sh, (int)sh.len - 1);
     }
     if (pre.n == 0 || k == 1) return;
     // boundary windows: rebuild the rolling state from the carried symbols, then feed tile symbols until
@@ -657,7 +674,7 @@ struct KpcTileMachine {
     const uint64_t line_start = sh.tile_in.last_nl;
     int used = 0;
     for (int i = 0; i < (int)sh.len && used < k - 1; ++i) {
-      uint8_t x = sh.cls[i];
+      uint8_t x = sh.cls[Shared::px(i)];
       if (x == KPC_CLS_SKIP) continue;
       if (x == KPC_CLS_BREAK) break;
       push(w, x, k, mask_f);
