@@ -156,6 +156,7 @@ KpcEngine::~KpcEngine() {
   }
   rt_dfree(d_shard_nl_); rt_hfree(h_shard_nl_); rt_hfree(h_shard_carry_);
   rt_dfree(desc_); rt_dfree(tile_counter_); rt_dfree(d_tmp_); rt_hfree(h_tmp_);
+  if (d_per_rec_) { rt_dfree(d_per_rec_); rt_hfree(h_per_rec_); }
   rt_dfree(scratch_); rt_dfree(scratch2_); rt_dfree(sort_buf_);
   if (h_out_) rt_hfree(h_out_);
   rt_dfree(dense_lo_); rt_dfree(dense_hi_);
@@ -1498,16 +1499,28 @@ void KpcEngine::tuple_flush(bool input_done) {
     rt_d2h(h_tmp_ + 6, d_tmp_ + 6, 8, compute_);
     rt_stream_sync(compute_);
     const uint64_t n_entries = h_tmp_[6];
-    // the tuple arrays are now sorted by record: those of records >= g_hi stay buffered
-    std::vector<uint32_t> hrecs(n);
-    rt_d2h(hrecs.data(), trecs_, n * 4, compute_);
-    std::vector<uint32_t> hrec_e(n_entries);
-    if (n_entries) rt_d2h(hrec_e.data(), erec, n_entries * 4, compute_);
-    rt_stream_sync(compute_);
-    keep_from = (uint64_t)(std::lower_bound(hrecs.begin(), hrecs.end(), (uint32_t)g_hi) - hrecs.begin());
-    n_final = (uint64_t)(std::lower_bound(hrec_e.begin(), hrec_e.end(), (uint32_t)g_hi) - hrec_e.begin());
-    for (uint64_t i = 0; i < n_final; ++i)
-      if (hrec_e[i] >= g_lo) per_rec[hrec_e[i] - g_lo]++;
+    // the tuple arrays are now sorted by record: those of records >= g_hi stay buffered.  Where the cut falls and how
+    // many entries every record has is worked out on the device (two binary searches + a histogram over the entries)
+    if (nrec) {
+      const size_t need = (nrec + 2) * sizeof(unsigned long long);
+      if (need > per_rec_cap_) {
+        rt_stream_sync(compute_);
+        if (d_per_rec_) { rt_dfree(d_per_rec_); rt_hfree(h_per_rec_); }
+        per_rec_cap_ = need * 2;
+        d_per_rec_ = (unsigned long long *)rt_dmalloc(per_rec_cap_);
+        h_per_rec_ = (unsigned long long *)rt_hmalloc(per_rec_cap_);
+      }
+      kpc_k_tuple_bounds(trecs_, n, erec, n_entries, (uint32_t)g_lo, (uint32_t)g_hi, d_per_rec_, d_per_rec_ + 2, compute_);
+      ++launches_;
+      rt_d2h(h_per_rec_, d_per_rec_, need, compute_);
+      rt_stream_sync(compute_);
+      keep_from = h_per_rec_[0];
+      n_final = h_per_rec_[1];
+      for (uint64_t j = 0; j < nrec; ++j) per_rec[j] = h_per_rec_[2 + j];
+    } else {
+      keep_from = 0;
+      n_final = 0;
+    }
   }
   // ---- order inside each record: Hashtbl.iter with the bucket count the table has at that point ----
   const int bits = sbits_ * cfg_.k;

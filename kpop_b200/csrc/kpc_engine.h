@@ -214,6 +214,8 @@ class KpcEngine {
   uint32_t *tile_counter_ = nullptr;
   uint32_t epoch_ = 0;
   unsigned long long *d_tmp_ = nullptr;  // 8 x u64 device scalars
+  unsigned long long *d_per_rec_ = nullptr, *h_per_rec_ = nullptr;  // -L: [0] tuples kept, [1] entries final, [2..] entries per record
+  size_t per_rec_cap_ = 0;
   unsigned long long *h_tmp_ = nullptr;  // pinned mirror
   void *scratch_ = nullptr;
   size_t scratch_cap_ = 0;

@@ -639,6 +639,31 @@ struct HeadWrite {
 __global__ void fill_u64_kernel(unsigned long long *a, unsigned long long v, uint64_t n) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) a[i] = v;
 }
+__device__ static unsigned long long lower_bound_u32(const uint32_t *a, unsigned long long n, uint32_t v) {
+  unsigned long long lo = 0, hi = n;
+  while (lo < hi) {
+    const unsigned long long mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__global__ void __launch_bounds__(256) tuple_bounds_kernel(const uint32_t *trecs, unsigned long long n, const uint32_t *erec,
+                                                           unsigned long long n_entries, uint32_t g_lo, uint32_t g_hi,
+                                                           unsigned long long *bounds, unsigned long long *per_rec) {
+  if (blockIdx.x == 0 && threadIdx.x < 2)
+    bounds[threadIdx.x] = threadIdx.x == 0 ? lower_bound_u32(trecs, n, g_hi) : lower_bound_u32(erec, n_entries, g_hi);
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_entries; i += stride) {
+    const uint32_t r = erec[i];
+    if (r >= g_lo && r < g_hi) atomicAdd(per_rec + (r - g_lo), 1ull);
+  }
+}
+void kpc_k_tuple_bounds(const uint32_t *trecs, uint64_t n, const uint32_t *erec, uint64_t n_entries, uint32_t g_lo,
+                        uint32_t g_hi, unsigned long long *bounds, unsigned long long *per_rec, rt_stream s) {
+  CUDA_CHECK(cudaMemsetAsync(per_rec, 0, (size_t)(g_hi - g_lo) * sizeof(unsigned long long), cs(s)));
+  tuple_bounds_kernel<<<ew_grid(n_entries ? n_entries : 1), 256, 0, cs(s)>>>(trecs, n, erec, n_entries, g_lo, g_hi, bounds, per_rec);
+  CUDA_CHECK(cudaGetLastError());
+}
 void kpc_k_tuple_reduce(unsigned long long *keys, unsigned long long *ranks, uint32_t *recs, uint64_t n,
                         unsigned long long *okeys, unsigned long long *ocounts, unsigned long long *oranks,
                         uint32_t *orecs, unsigned long long *n_out, void *scratch, rt_stream s) {

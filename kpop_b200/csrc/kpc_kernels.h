@@ -90,6 +90,10 @@ void kpc_k_order_entries(unsigned long long *keys, unsigned long long *counts, u
                          uint32_t rec_off, void *scratch, rt_stream s);
 // -L: sort tuples by (rec, key), then run-length: one entry per distinct (rec, key) with its count and min rank.
 // *n_out = number of entries.  Output arrays must hold n items.
+// -L bookkeeping on the device: bounds[0] = tuples (sorted by record) of records < g_hi, bounds[1] = entries of records
+// < g_hi; per_rec[r - g_lo] = entries of record r for g_lo <= r < g_hi (per_rec zeroed here)
+void kpc_k_tuple_bounds(const uint32_t *trecs, uint64_t n, const uint32_t *erec, uint64_t n_entries, uint32_t g_lo,
+                        uint32_t g_hi, unsigned long long *bounds, unsigned long long *per_rec, rt_stream s);
 void kpc_k_tuple_reduce(unsigned long long *keys, unsigned long long *ranks, uint32_t *recs, uint64_t n,
                         unsigned long long *okeys, unsigned long long *ocounts, unsigned long long *oranks,
                         uint32_t *orecs, unsigned long long *n_out, void *scratch, rt_stream s);

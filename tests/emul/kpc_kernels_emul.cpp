@@ -164,6 +164,14 @@ void kpc_k_order_entries(unsigned long long *keys, unsigned long long *counts, u
   for (uint64_t i = 0; i < n; ++i) { k2[i] = keys[idx[i]]; c2[i] = counts[idx[i]]; r2[i] = ranks[idx[i]]; if (recs) e2[i] = recs[idx[i]]; }
   for (uint64_t i = 0; i < n; ++i) { keys[i] = k2[i]; counts[i] = c2[i]; ranks[i] = r2[i]; if (recs) recs[i] = e2[i]; }
 }
+void kpc_k_tuple_bounds(const uint32_t *trecs, uint64_t n, const uint32_t *erec, uint64_t n_entries, uint32_t g_lo,
+                        uint32_t g_hi, unsigned long long *bounds, unsigned long long *per_rec, rt_stream) {
+  bounds[0] = (unsigned long long)(std::lower_bound(trecs, trecs + n, g_hi) - trecs);
+  bounds[1] = (unsigned long long)(std::lower_bound(erec, erec + n_entries, g_hi) - erec);
+  for (uint32_t r = g_lo; r < g_hi; ++r) per_rec[r - g_lo] = 0;
+  for (uint64_t i = 0; i < n_entries; ++i)
+    if (erec[i] >= g_lo && erec[i] < g_hi) per_rec[erec[i] - g_lo]++;
+}
 void kpc_k_tuple_reduce(unsigned long long *keys, unsigned long long *ranks, uint32_t *recs, uint64_t n,
                         unsigned long long *okeys, unsigned long long *ocounts, unsigned long long *oranks,
                         uint32_t *orecs, unsigned long long *n_out, void *, rt_stream) {
