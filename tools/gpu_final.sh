@@ -13,7 +13,8 @@ PY
 head -c 600000 /tmp/g0.fa > /tmp/g0s.fa
 for spec in "memcheck -k 30 -l G0 -f /tmp/g0s.fa" "memcheck -k 5 -L -f /tmp/c1.fa" "racecheck -k 30 -l G0 -f /tmp/g0s.fa"; do
   set -- $spec; tool=$1; shift
-  timeout 600 compute-sanitizer --tool $tool kpop_b200/bin/KPopCount "$@" 2>&1 >/dev/null | tail -n 2 | sed "s|^|[$tool $*] |" | tee -a gpurun_out/sanitizer_other_paths.log
+  timeout 600 compute-sanitizer --tool $tool --log-file /tmp/san.log kpop_b200/bin/KPopCount "$@" > /dev/null 2>&1
+  tail -n 1 /tmp/san.log | sed "s|^|[$tool $*] |" | tee -a gpurun_out/sanitizer_other_paths.log
 done
 ( timeout 600 python tools/bench_configs.py 2>&1 ) > gpurun_out/configs.jsonl
 bash tools/gpu_c4.sh > /dev/null 2>&1
