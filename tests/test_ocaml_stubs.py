@@ -46,3 +46,18 @@ def test_compute_iterates_the_reference_input_list():
     assert "Files.Type.t list" in ml and "List.iter" in ml and "iter_files" not in ml
     for ctor in ("Files.Type.FASTA", "SingleEndFASTQ", "PairedEndFASTQ"):
         assert ctor in ml
+
+
+def test_every_stub_is_bound_and_every_identifier_the_driver_uses_is_declared():
+    ml = open(os.path.join(OCAML, "Kpc_gpu.ml")).read()
+    c = open(os.path.join(OCAML, "kpc_stubs.c")).read()
+    drv = open(os.path.join(OCAML, "KPopCount_gpu.ml")).read()
+    bound = set(re.findall(r"=\s*\"(kpc_ml_\w+)\"", ml))
+    stubs = set(re.findall(r"^value (kpc_ml_\w+)\(", c, flags=re.M))
+    assert stubs == bound, (stubs - bound, bound - stubs)
+    # values, types and constructors Kpc_gpu.ml offers
+    declared = set(re.findall(r"external\s+(\w+)\s*:", ml)) | set(re.findall(r"^type\s+(\w+)", ml, flags=re.M))
+    for rhs in re.findall(r"^type\s+\w+\s*=\s*([A-Z][\w\s|]*)$", ml, flags=re.M):
+        declared |= {x.strip() for x in rhs.split("|")}
+    used = set(re.findall(r"\bKpc_gpu\.(\w+)", drv))
+    assert used and used <= declared, used - declared
