@@ -9,8 +9,11 @@
 // One CTA of NT threads owns one tile of TB = 16 * VPT * NT bytes at a time (claimed in stream order):
 //   0. the tile (and the 16 bytes before it) arrives in shared memory by ONE bulk copy (cp.async.bulk, completion on an
 //      mbarrier) that thread 0 started as soon as the previous tile's bytes had been read for the last time
-//   1. census: every thread owns 16 * VPT consecutive bytes; three integer operations per word flag the line feeds, dot
-//      products gather the flags into a bit mask that stays in registers; one warp scan + one 16-entry scan rank them
+//   1. census, taken one tile AHEAD straight from L2: every thread owns 16 * VPT consecutive bytes of the tile; the loads
+//      are 256 bits wide and laid out so that a warp's load instruction covers whole 128-byte lines (lane L takes sector
+//      L, the per-sector masks reach their owners by shuffles): what such scattered accesses cost is the number of
+//      sector requests, not the bytes.  Three integer operations per word flag the line feeds, dot products gather the
+//      flags into a bit mask that stays in registers; one warp scan + one 16-entry scan rank them
 //   2. warp 0 publishes the tile's line-feed count and gets the number of line feeds before the tile by a decoupled
 //      look-back over one word per tile (the other warps use the time for the bucket copy-out that is still pending)
 //   3. every line feed knows its line number: the thread that holds it writes the start / the end of the sequence
@@ -24,7 +27,7 @@
 //      predicated STS.U16, no branch)
 //   6. software write-combining: after every round the thread that owns a slice reserves whole 32-byte chunks of its
 //      bucket in the slice's queue in HBM (one global atomic, issued a round before its result is needed) and copies
-//      them out with 128-bit accesses.  A bucket or queue that overflows (skewed input) sends its keys to the global
+//      them out, one 256-bit store (a whole sector) per chunk.  A bucket or queue that overflows (skewed input) sends its keys to the global
 //      table with RED, so the result is exact for any input.
 //
 // The source is compiled by nvcc for sm_100a (the product) and by g++ against tests/emul/simt_emul.h (KPC_SIMT_EMUL,
