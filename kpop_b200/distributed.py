@@ -8,6 +8,8 @@ only care needed is counter width: the per-rank tables are u32 and their sum may
 import torch
 import torch.distributed as dist
 
+from . import _native as N
+
 U32_LIMIT = 1 << 32
 
 
@@ -254,6 +256,153 @@ def count_fastq_sharded(path, k=12, label="sample", device=None, group=None, chu
         torch.cuda.current_stream().wait_stream(lib_stream)
         reduce_dense_tables(lo_t, promote, kc.dense_max(), group, has_hi=kc.dense_has_hi())
         torch.cuda.synchronize()
+        if rank == 0:
+            kc.finish()
+            text = kc.take_text()
+    return text
+
+
+# ------------------------------------------------------------------------------------------------------------
+# read-chunk sharding of a PAIR of FASTQ files ("both mate files must be cut at the same record index")
+# ------------------------------------------------------------------------------------------------------------
+def _nth_line_feed(path, lo, hi, n, block=8 << 20):
+    """File offset of the n-th (1-based) line feed of [lo, hi), or -1."""
+    import numpy as np
+    with open(path, "rb") as f:
+        pos = lo
+        while pos < hi:
+            f.seek(pos)
+            b = np.frombuffer(f.read(min(block, hi - pos)), dtype=np.uint8)
+            if b.size == 0:
+                break
+            nz = np.flatnonzero(b == 10)
+            if n <= nz.size:
+                return pos + int(nz[n - 1])
+            n -= int(nz.size)
+            pos += b.size
+    return -1
+
+
+def _all_reduce_max_i64(values, world_size, group):
+    if world_size == 1:
+        return [int(v) for v in values]
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return [int(x) for x in t.tolist()]
+
+
+def pair_aligned_ranges(path1, path2, group=None, rank=None, world_size=None):
+    """((start1, end1), (start2, end2), first_pair, n_pairs): the byte ranges of the two mate files that hold the SAME
+    pairs [first_pair, first_pair + n_pairs) for this rank; over the ranks the pairs tile [0, P), P = the number of
+    complete records of the shorter file (FASTQ.iter_pe stops there, Files.ml:228-247; what lies behind is never read).
+
+    Two exchanges of a few integers per rank: (1) every rank counts the line feeds of its tentative byte range of both
+    files -> total lines -> P and the pair every rank starts with; (2) the rank whose tentative range holds the line feed
+    that ends line 4 * boundary - 1 of a file looks its offset up; a MAX all-reduce hands every offset to everybody."""
+    import os
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world_size is None:
+        world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+    paths = (path1, path2)
+    sizes = [os.path.getsize(p) for p in paths]
+    tent = [_tentative_range(sizes[f], world_size, rank) for f in (0, 1)]
+    mine = [_host_census(paths[f], tent[f][0], tent[f][1], want_first=0)[0] for f in (0, 1)]
+    counts = [_all_gather_i64(mine[f], rank, world_size, group) for f in (0, 1)]
+    records = []
+    for f in (0, 1):
+        lines = sum(counts[f])
+        if sizes[f]:
+            with open(paths[f], "rb") as fh:
+                fh.seek(sizes[f] - 1)
+                if fh.read(1) != b"\n":
+                    lines += 1                 # input_line returns a last line without line feed like any other
+        records.append(lines // 4)             # an incomplete last record is dropped (Files.ml:217)
+    n_total = min(records)
+    bounds = [shard_records(n_total, world_size, r)[0] for r in range(world_size)] + [n_total]
+    # offset of the first byte of record b of file f = one past the line feed number 4 b (1-based)
+    want = []
+    for f in (0, 1):
+        before = sum(counts[f][:rank])         # line feeds before this rank's tentative range
+        for b in bounds:
+            off = -1
+            if b == 0:
+                off = 0
+            else:
+                nth = 4 * b
+                if before < nth <= before + mine[f]:
+                    off = _nth_line_feed(paths[f], tent[f][0], tent[f][1], nth - before) + 1
+                elif nth > sum(counts[f]) and rank == world_size - 1:
+                    off = sizes[f]             # the last record of the file ends without a line feed
+            want.append(off)
+    offs = _all_reduce_max_i64(want, world_size, group)
+    n = world_size + 1
+    r1 = (offs[rank], offs[rank + 1])
+    r2 = (offs[n + rank], offs[n + rank + 1])
+    if min(r1 + r2) < 0:
+        raise RuntimeError("internal: a pair boundary was not located")
+    return r1, r2, bounds[rank], bounds[rank + 1] - bounds[rank]
+
+
+def count_fastq_pair_sharded(path1, path2, k=12, label="sample", device=0, group=None, lib=None, chunk_bytes=64 << 20):
+    """KPopCount -k K -l LABEL -p PATH1 PATH2 on all the ranks of the process group, dense-table configurations: every rank
+    counts the same range of PAIRS out of both files (pair_aligned_ranges), the tables are summed, rank 0 formats.  In the
+    dense table the order of the mates does not matter (sums commute); what has to be exact is which records belong to a
+    pair at all.  Returns the text on rank 0, None elsewhere."""
+    from .counter import KMerCounter
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    (s1, e1), (s2, e2), first_pair, _n = pair_aligned_ranges(path1, path2, group, rank, world)
+    text, err = None, None
+    with KMerCounter(k=k, label=label, device=device, lib=lib) as kc:
+        try:
+            kc.begin("paired-end")
+            with open(path1, "rb") as f1, open(path2, "rb") as f2:
+                pos, end, fh = [s1, s2], [e1, e2], [f1, f2]
+                done = [False, False]
+                while not all(done):
+                    for m in (0, 1):
+                        if done[m]:
+                            continue
+                        fh[m].seek(pos[m])
+                        data = fh[m].read(min(chunk_bytes, end[m] - pos[m]))
+                        pos[m] += len(data)
+                        done[m] = pos[m] >= end[m]
+                        kc.feed(data, mate=m, eof=done[m])
+            kc.end()
+        except Exception as e:  # noqa: BLE001 -- shared with the other ranks below
+            err = e
+        # a malformed pair: the reference stops at the FIRST one and names the last of its eight lines, counted over both
+        # files (Files.ml:241-243); a shard reports lines of its own range, so the number is moved and the smallest wins
+        bad_line = 0
+        if err is not None and getattr(err, "code", None) == N.KPC_E_MALFORMED_FASTQ:
+            import re
+            m = re.search(r"On line (\d+):", err.message)
+            if m:
+                bad_line = int(m.group(1)) + 8 * first_pair
+                err = None
+        lines = _all_gather_i64(bad_line, rank, world, group)
+        _raise_together(err, rank, world, group)
+        if any(lines):
+            from .counter import KPopCountError
+            raise KPopCountError(N.KPC_E_MALFORMED_FASTQ, "On line %d: Malformed FASTQ file" % min(x for x in lines if x))
+        lo, _hi, nbins = kc.dense_table()
+        if kc.backend() == "cuda":
+            lo_t, promote = table_views(kc)
+        else:                                  # test-only emulation: the table is host memory
+            import ctypes
+            import numpy as np
+            lo_t = torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(lo, ctypes.POINTER(ctypes.c_int32)), shape=(nbins,)))
+
+            def promote():
+                kc.dense_promote()
+                _lo, hi, n = kc.dense_table()
+                return torch.from_numpy(np.ctypeslib.as_array(ctypes.cast(hi, ctypes.POINTER(ctypes.c_int64)), shape=(n,)))
+        kc.sync()
+        reduce_dense_tables(lo_t, promote, kc.dense_max(), group, has_hi=kc.dense_has_hi())
+        if kc.backend() == "cuda":
+            torch.cuda.synchronize()
         if rank == 0:
             kc.finish()
             text = kc.take_text()

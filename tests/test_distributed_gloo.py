@@ -3,6 +3,7 @@ including the switch to a 64-bit reduction when a u32 sum could wrap.  The per-s
 (oracle/fast_dense.cpp); on the GPU box the same functions are driven by bench.py with the device tables."""
 import ctypes
 import os
+import re
 import subprocess
 import sys
 
@@ -161,3 +162,78 @@ def test_sparse_merge_of_a_sharded_sample_equals_one_process(tmp_path, world, k)
     want = subprocess.run([os.path.join(ORACLE_DIR, "_build", "kpopcount_oracle"), "-k", str(k), "-l", "x", "-s", str(path)],
                           stdout=subprocess.PIPE, check=True).stdout
     assert (tmp_path / "sparse.txt").read_bytes() == want
+
+
+# ---- a PAIR of FASTQ files on several ranks (both files cut at the same record index) ---------------------
+def _pair_worker(rank, world, port, p1, p2, tmp, k):
+    sys.path.insert(0, ROOT)
+    from kpop_b200 import _native
+    from kpop_b200.distributed import count_fastq_pair_sharded, pair_aligned_ranges
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["KPC_EMUL_TILE"] = "64x16"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = _native.load(os.path.join(ROOT, "tests", "emul", "_build", "libkpopcount_emul.so"))
+    r1, r2, first, n = pair_aligned_ranges(p1, p2)
+    with open(os.path.join(tmp, "ranges.%d" % rank), "w") as f:
+        f.write("%d %d %d %d %d %d\n" % (r1 + r2 + (first, n)))
+    try:
+        text = count_fastq_pair_sharded(p1, p2, k=k, label="x", lib=lib, chunk_bytes=3000)
+        if rank == 0:
+            with open(os.path.join(tmp, "pair.txt"), "wb") as f:
+                f.write(text)
+    except Exception as e:  # noqa: BLE001 -- every rank must see the same failure
+        with open(os.path.join(tmp, "error.%d" % rank), "w") as f:
+            f.write(str(e))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _mates(rng, n, tag, unterminated=False, bad_at=None):
+    out = []
+    for i in range(n):
+        ln = rng.randint(15, 70)
+        seq = bytes(rng.choices(b"ACGTN", weights=[20, 20, 20, 20, 1], k=ln))
+        head = b"@r%d/%d" % (i, tag) if i != bad_at else b"r%d/%d" % (i, tag)
+        out.append(head + b"\n" + seq + b"\n+\n" + bytes(rng.choice(b"@+I") for _ in range(ln)) + b"\n")
+    data = b"".join(out)
+    return data[:-1] if unterminated and data else data
+
+
+@pytest.mark.parametrize("world,n1,n2,unterminated,bad", [(2, 120, 90, False, None), (3, 75, 75, True, None), (3, 2, 40, False, None),
+                                                          (2, 100, 130, False, (1, 77)), (3, 90, 60, True, (0, 5))])
+def test_paired_files_cut_at_the_same_pair_on_every_rank(tmp_path, world, n1, n2, unterminated, bad):
+    """pair_aligned_ranges: the ranks' ranges of the two files hold the same pairs, tile exactly the part of each file that
+    FASTQ.iter_pe reads (up to the end of the shorter file's last complete record), and the summed dense tables print what
+    ONE KPopCount -p prints -- including the line number of the first malformed pair."""
+    import random
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "emul")], check=True)
+    rng = random.Random(world * 1000 + n1 + n2)
+    m1 = _mates(rng, n1, 1, unterminated, bad[1] if bad and bad[0] == 0 else None)
+    m2 = _mates(rng, n2, 2, unterminated, bad[1] if bad and bad[0] == 1 else None)
+    p1, p2 = tmp_path / "m1.fq", tmp_path / "m2.fq"
+    p1.write_bytes(m1); p2.write_bytes(m2)
+    port = 35000 + (os.getpid() % 2000) + world + n1
+    mp.spawn(_pair_worker, args=(world, port, str(p1), str(p2), str(tmp_path), 9), nprocs=world, join=True)
+    ranges = [tuple(int(x) for x in open(tmp_path / ("ranges.%d" % r)).read().split()) for r in range(world)]
+    pairs = min(n1, n2)
+    assert ranges[0][0] == 0 and ranges[0][2] == 0 and ranges[0][4] == 0
+    for r in range(world):
+        s1, e1, s2, e2, first, n = ranges[r]
+        assert m1[s1:e1].count(b"\n") + (1 if unterminated and e1 == len(m1) and e1 > s1 else 0) == 4 * n
+        assert m2[s2:e2].count(b"\n") + (1 if unterminated and e2 == len(m2) and e2 > s2 else 0) == 4 * n
+        if r + 1 < world:
+            assert (e1, e2, first + n) == (ranges[r + 1][0], ranges[r + 1][2], ranges[r + 1][4])
+        else:
+            assert first + n == pairs
+    oracle = subprocess.run([os.path.join(ORACLE_DIR, "_build", "kpopcount_oracle"), "-k", "9", "-l", "x", "-p", str(p1), str(p2)],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    if bad is None or bad[1] >= pairs:
+        assert oracle.returncode == 0
+        assert (tmp_path / "pair.txt").read_bytes() == oracle.stdout
+    else:
+        assert oracle.returncode == 2
+        want_line = re.search(rb"On line (\d+)", oracle.stderr).group(1).decode()
+        for r in range(world):
+            assert ("On line %s:" % want_line) in open(tmp_path / ("error.%d" % r)).read()
