@@ -332,7 +332,10 @@ def pair_aligned_ranges(path1, path2, group=None, rank=None, world_size=None):
             else:
                 nth = 4 * b
                 if before < nth <= before + mine[f]:
-                    off = _nth_line_feed(paths[f], tent[f][0], tent[f][1], nth - before) + 1
+                    at = _nth_line_feed(paths[f], tent[f][0], tent[f][1], nth - before)
+                    if at < 0:
+                        raise RuntimeError("%s changed while it was being cut" % paths[f])
+                    off = at + 1
                 elif nth > sum(counts[f]) and rank == world_size - 1:
                     off = sizes[f]             # the last record of the file ends without a line feed
             want.append(off)
