@@ -523,3 +523,89 @@ def count_fastq_sharded_sparse(path, k=21, label="sample", device=0, group=None,
     parts = [None] * world
     dist.all_gather_object(parts, mine, group=group)
     return header + b"".join(parts) if rank == 0 else None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# -L (one spectrum per read) on all the ranks ("-L mode shards by records")
+# ------------------------------------------------------------------------------------------------------------
+def _longest_line(path, lo, hi, block=8 << 20):
+    """Length of the longest line that has a byte in [lo, hi) (pieces cut by the range ends count as they are)."""
+    import numpy as np
+    longest, run = 0, 0
+    with open(path, "rb") as f:
+        pos = lo
+        while pos < hi:
+            f.seek(pos)
+            b = np.frombuffer(f.read(min(block, hi - pos)), dtype=np.uint8)
+            if b.size == 0:
+                break
+            nz = np.flatnonzero(b == 10)
+            if nz.size == 0:
+                run += int(b.size)
+            else:
+                longest = max(longest, run + int(nz[0]))
+                if nz.size > 1:
+                    longest = max(longest, int(np.max(np.diff(nz))) - 1)
+                run = int(b.size) - int(nz[-1]) - 1
+            pos += b.size
+    return max(longest, run)
+
+
+def count_fastq_sharded_per_record(path, k=12, content=None, device=0, group=None, max_results_size=16777216, lib=None,
+                                   chunk_bytes=32 << 20):
+    """KPopCount -k K -L -s PATH on all the ranks of the process group: every rank prints the spectra of the records in
+    its record-aligned byte range, rank 0 returns the concatenation in rank order (= record order), the others None.
+
+    A record's spectrum depends on nothing but the record -- except through the bucket count of the reference's table,
+    which only ever grows (when one record holds more than twice as many distinct k-mers as there are buckets) and then
+    changes the order of every later spectrum.  That cannot happen when 2 * buckets >= the longest line of the file, which
+    is checked here (the default -M gives 2^24 buckets); otherwise the call refuses instead of guessing."""
+    from .counter import Content, KMerCounter, KPopCountError
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    start, end = shard_fastq_byte_range(path, group, rank, world)
+    buckets = 16
+    while buckets < max_results_size:
+        buckets *= 2
+    longest = max(_all_gather_i64(_longest_line(path, start, end), rank, world, group))
+    if longest > 2 * buckets:
+        raise KPopCountError(-9, "a record of %d bytes could make the table of %d buckets grow: its later spectra would "
+                                 "depend on earlier shards" % (longest, buckets))
+    err, mine, bad_line = None, b"", 0
+    with KMerCounter(k=k, content=Content.DNA_ds if content is None else content, label="", device=device, lib=lib,
+                     max_results_size=max_results_size) as kc:
+        try:
+            kc.begin("single-end")
+            with open(path, "rb") as f:
+                f.seek(start)
+                pos = start
+                if end == start:
+                    kc.feed(b"", eof=True)
+                while pos < end:
+                    b = f.read(min(chunk_bytes, end - pos))
+                    pos += len(b)
+                    kc.feed(b, eof=(pos >= end))
+            kc.end()
+            kc.finish()
+        except Exception as e:  # noqa: BLE001 -- shared with the other ranks below
+            err = e
+        mine = kc.take_text() if err is None or getattr(err, "code", None) == N.KPC_E_MALFORMED_FASTQ else b""
+    # a malformed record: the reference prints every spectrum before it, then fails with its line number (Files.ml:213)
+    if err is not None and getattr(err, "code", None) == N.KPC_E_MALFORMED_FASTQ:
+        import re
+        m = re.search(r"On line (\d+):", err.message)
+        if m:
+            bad_line = int(m.group(1)) + 4 * record_aligned_ranges.first_record
+            err = None
+    lines = _all_gather_i64(bad_line, rank, world, group)
+    _raise_together(err, rank, world, group)
+    parts = [mine]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine, group=group)
+    if any(lines):
+        first_bad = min(r for r in range(world) if lines[r])
+        e = KPopCountError(N.KPC_E_MALFORMED_FASTQ, "On line %d: Malformed FASTQ file" % lines[first_bad])
+        e.partial_text = b"".join(parts[: first_bad + 1])   # what the reference had printed when it failed
+        raise e
+    return b"".join(parts) if rank == 0 else None

@@ -237,3 +237,55 @@ def test_paired_files_cut_at_the_same_pair_on_every_rank(tmp_path, world, n1, n2
         want_line = re.search(rb"On line (\d+)", oracle.stderr).group(1).decode()
         for r in range(world):
             assert ("On line %s:" % want_line) in open(tmp_path / ("error.%d" % r)).read()
+
+
+# ---- -L (one spectrum per read) on several ranks --------------------------------------------------------------------------
+def _per_record_worker(rank, world, port, path, tmp, k, m):
+    sys.path.insert(0, ROOT)
+    from kpop_b200 import _native
+    from kpop_b200.distributed import count_fastq_sharded_per_record
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["KPC_EMUL_TILE"] = "64x16"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = _native.load(os.path.join(ROOT, "tests", "emul", "_build", "libkpopcount_emul.so"))
+    try:
+        text = count_fastq_sharded_per_record(path, k=k, lib=lib, max_results_size=m, chunk_bytes=5000)
+        if rank == 0:
+            with open(os.path.join(tmp, "L.txt"), "wb") as f:
+                f.write(text)
+    except Exception as e:  # noqa: BLE001
+        with open(os.path.join(tmp, "error.%d" % rank), "wb") as f:
+            f.write(str(e).encode() + b"\n" + getattr(e, "partial_text", b""))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,bad,m", [(2, 150, None, 16777216), (3, 101, None, 4096), (3, 120, 83, 16777216), (2, 60, None, 8)])
+def test_per_record_spectra_of_a_sharded_file(tmp_path, world, n, bad, m):
+    """-L shards by records: the ranks' texts, concatenated in rank order, are what ONE KPopCount -L prints; a
+    malformed record stops the run after the spectra before it, with the reference's line number; a table that could grow
+    inside the run (tiny -M) is refused on every rank."""
+    import random
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "emul")], check=True)
+    rng = random.Random(world * 100 + n)
+    path = tmp_path / "reads.fq"
+    path.write_bytes(_mates(rng, n, 1, False, bad))
+    port = 37000 + (os.getpid() % 2000) + world + n
+    mp.spawn(_per_record_worker, args=(world, port, str(path), str(tmp_path), 7, m), nprocs=world, join=True)
+    oracle = subprocess.run([os.path.join(ORACLE_DIR, "_build", "kpopcount_oracle"), "-k", "7", "-L", "-M", str(m), "-s", str(path)],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    if m == 8:
+        for r in range(world):
+            assert b"could make the table" in open(tmp_path / ("error.%d" % r), "rb").read()
+    elif bad is None:
+        assert oracle.returncode == 0
+        assert (tmp_path / "L.txt").read_bytes() == oracle.stdout
+    else:
+        assert oracle.returncode == 2
+        want_line = re.search(rb"On line (\d+)", oracle.stderr).group(1)
+        for r in range(world):
+            msg, _, partial = open(tmp_path / ("error.%d" % r), "rb").read().partition(b"\n")
+            assert b"On line " + want_line + b":" in msg
+            assert partial == oracle.stdout          # the spectra the reference had printed before it failed
