@@ -7,7 +7,8 @@ The package holds only what that path needs:
 * ``_native``          ctypes binding of the C ABI (fails loudly when the library or a GPU is missing);
 * ``counter``          ``KMerCounter``: the host-side mirror of the reference's ``KMerCounter.compute`` functor
                        (bin/KPopCount.ml:20-64) on top of the C ABI;
-* ``distributed``      read-chunk sharding across the GPUs of one box and the NCCL table reduce.
+* ``distributed``      one process per GPU: read-chunk sharding of one file / of a pair of files, the NCCL table
+                       reduce, the sparse merge for large k, ``-L`` spectra gathered in record order.
 
 There is no CPU fallback anywhere in this package.
 """
