@@ -54,6 +54,9 @@
 #ifndef FQ_L2HINTS
 #define FQ_L2HINTS 1        // census loads evict_last, the tile's bulk copy evict_first
 #endif
+// measurement-only builds (never the product): FQ_PHASE_CLOCKS adds clock() probes at the phase boundaries
+// (tools/gpu_phase_clocks.sh); FQ_X_NOATOM / FQ_X_NOSTG drop the queue atomics / the queue stores to see what they cost --
+// the results are then WRONG, only the timing means something
 #ifdef FQ_PHASE_CLOCKS
 __device__ unsigned long long g_fq_phase[16];
 #define FQ_PROBE(i) do { if (tid == 32) { const uint32_t c_ = (uint32_t)clock(); S.dbg[i] += c_ - S.dbg_last; S.dbg_last = c_; } } while (0)
