@@ -265,6 +265,13 @@ def count_fastq_sharded(path, k=12, label="sample", device=None, group=None, chu
 # ------------------------------------------------------------------------------------------------------------
 # read-chunk sharding of a PAIR of FASTQ files ("both mate files must be cut at the same record index")
 # ------------------------------------------------------------------------------------------------------------
+def _default_device(device):
+    """The GPU of this rank when the caller names none: torch's current device (torchrun scripts set it per rank)."""
+    if device is not None:
+        return device
+    return torch.cuda.current_device() if torch.cuda.is_available() else 0
+
+
 def _nth_line_feed(path, lo, hi, n, block=8 << 20):
     """File offset of the n-th (1-based) line feed of [lo, hi), or -1."""
     import numpy as np
@@ -348,7 +355,7 @@ def pair_aligned_ranges(path1, path2, group=None, rank=None, world_size=None):
     return r1, r2, bounds[rank], bounds[rank + 1] - bounds[rank]
 
 
-def count_fastq_pair_sharded(path1, path2, k=12, label="sample", device=0, group=None, lib=None, chunk_bytes=64 << 20):
+def count_fastq_pair_sharded(path1, path2, k=12, label="sample", device=None, group=None, lib=None, chunk_bytes=64 << 20):
     """KPopCount -k K -l LABEL -p PATH1 PATH2 on all the ranks of the process group, dense-table configurations: every rank
     counts the same range of PAIRS out of both files (pair_aligned_ranges), the tables are summed, rank 0 formats.  In the
     dense table the order of the mates does not matter (sums commute); what has to be exact is which records belong to a
@@ -356,6 +363,7 @@ def count_fastq_pair_sharded(path1, path2, k=12, label="sample", device=0, group
     from .counter import KMerCounter
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    device = _default_device(device)
     (s1, e1), (s2, e2), first_pair, _n = pair_aligned_ranges(path1, path2, group, rank, world)
     text, err = None, None
     with KMerCounter(k=k, label=label, device=device, lib=lib) as kc:
@@ -551,7 +559,7 @@ def _longest_line(path, lo, hi, block=8 << 20):
     return max(longest, run)
 
 
-def count_fastq_sharded_per_record(path, k=12, content=None, device=0, group=None, max_results_size=16777216, lib=None,
+def count_fastq_sharded_per_record(path, k=12, content=None, device=None, group=None, max_results_size=16777216, lib=None,
                                    chunk_bytes=32 << 20):
     """KPopCount -k K -L -s PATH on all the ranks of the process group: every rank prints the spectra of the records in
     its record-aligned byte range, rank 0 returns the concatenation in rank order (= record order), the others None.
@@ -563,6 +571,7 @@ def count_fastq_sharded_per_record(path, k=12, content=None, device=0, group=Non
     from .counter import Content, KMerCounter, KPopCountError
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    device = _default_device(device)
     start, end = shard_fastq_byte_range(path, group, rank, world)
     buckets = 16
     while buckets < max_results_size:
